@@ -1,0 +1,155 @@
+/* verticut_gpu.h - C ABI of the B200-native VertiCut hot path (libverticut_gpu.so).
+ *
+ * This is the drop-in boundary for the MIH / linear-scan path of tu-dresden/verticut: plain
+ * pointers and sizes, no C++ or torch types.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference tree).  The C++ mirror of the reference's own classes
+ * (GpuTableProxy : BaseProxy, SearchWorker) lives in verticut_b200/host/ and calls only this ABI;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success unless stated otherwise; a negative value is an error
+ *    (VC_ERR_*), with text available from vc_last_error() (per host thread).
+ *  - a code is `code_bits/8` raw bytes, exactly the record of the reference's code files
+ *    (src/build_hash_tables.cc:40-45); the id of a code is `first_id` + its ordinal.
+ *  - table t keys on bytes [t*s/8, (t+1)*s/8) of the code, little-endian UNSIGNED
+ *    (Pilaf/image_tools.h:12-18 binaryToInt with its sign-extension bug removed).
+ *  - distance = sum of popcounts of the XOR (Pilaf/image_tools.h:21-33).
+ *  - search results are the k smallest packed words (dist << 32 | id)
+ *    (src/search_worker.cc:12-13,254-256) in ASCENDING order - the canonical tie rule "by id".
+ *    The reference emits descending distance (src/search_worker.cc:210-216); the C++ mirror
+ *    reverses.  Unused result slots hold 0xFFFFFFFF / VC_EMPTY_KEY.
+ *  - an index object may be used by one host thread at a time (the reference's proxies are
+ *    single-threaded too: src/pilaf_proxy.h:19-21); batches provide the parallelism.
+ *  - there is NO CPU fallback: without a CUDA device every call that computes fails with
+ *    VC_ERR_CUDA.
+ */
+#ifndef VERTICUT_GPU_H
+#define VERTICUT_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VC_ABI_VERSION 1
+
+/* return codes.  0/1 mirror src/base_proxy.h:10-13 (PROXY_FOUND 0 / PROXY_NOT_FOUND 1 /
+ * PROXY_PUT_DONE 0 / PROXY_PUT_FAIL 1). */
+#define VC_OK 0
+#define VC_NOT_FOUND 1
+#define VC_ERR_ARG (-1)     /* bad argument (shape, k, table id, null pointer) */
+#define VC_ERR_STATE (-2)   /* call not valid in this state (e.g. search before build) */
+#define VC_ERR_CUDA (-3)    /* CUDA runtime error / no device */
+#define VC_ERR_NOMEM (-4)   /* device or host allocation failed */
+
+#define VC_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define VC_EMPTY_U32 0xFFFFFFFFu
+#define VC_MAX_K 2048u
+#define VC_APPROXIMATE_FACTOR 20u /* src/search_worker.h:14 */
+
+typedef struct vc_index vc_index;
+
+/* Per-query statistics; mirrors SearchWorker::get_stat (src/search_worker.cc:24-30). */
+typedef struct vc_query_stats {
+  uint32_t radius;           /* last substring radius searched (radius_, search_worker.cc:217) */
+  uint32_t n_results;        /* entries returned (<= k) */
+  uint64_t probes;           /* bucket lookups issued, all tables (n_sub_reads_, search_worker.cc:245) */
+  uint64_t occupancy_tests;  /* occupancy-bitmap tests (n_local_reads_, search_worker.cc:239); s = 32 tables only */
+  uint64_t candidates;       /* members of the probed buckets, duplicates included */
+  uint64_t unique;           /* distinct candidates (knn_found_.size(), search_worker.cc:190); approximate mode only, else 0 */
+} vc_query_stats;
+
+typedef struct vc_index_info {
+  uint64_t n_codes;
+  uint32_t code_bits, n_tables, substring_bits, first_id;
+  int32_t device;
+  int32_t built;            /* tables are current */
+  uint64_t device_bytes;    /* HBM held by the index, tables included */
+} vc_index_info;
+
+const char* vc_last_error(void);
+int vc_abi_version(void);
+/* number of CUDA devices visible, or VC_ERR_CUDA */
+int vc_device_count(void);
+
+/* ---- index life cycle ------------------------------------------------------------------
+ * Replaces the KV servers behind BaseProxy::init/close (src/base_proxy.h:24-28): the tables live
+ * in the HBM of `device`.  code_bits in {64,128,256}; n_tables = 0 builds no tables (linear scan
+ * only), otherwise code_bits/n_tables must be 8, 16 or 32 (uint32 bucket index,
+ * src/search_worker.cc:165-167).  first_id = global id of the first code of this shard. */
+int vc_index_create(int device, uint32_t code_bits, uint32_t n_tables, uint32_t first_id, vc_index** out);
+void vc_index_destroy(vc_index* ix);
+int vc_index_get_info(const vc_index* ix, vc_index_info* info);
+
+/* Appends n codes from host memory (raw records); ids continue from the last one.  Replaces the
+ * fread loop of load_binarycode (src/build_hash_tables.cc:40-45,55,69).  Invalidates built tables. */
+int vc_index_add(vc_index* ix, const void* codes, uint64_t n);
+/* Appends n codes already in device memory of this index's device. */
+int vc_index_add_device(vc_index* ix, const void* d_codes, uint64_t n);
+/* Appends n synthetic codes generated on the device: 64-bit word w of code `id` is
+ * vc_synth_word(seed, id, w) (same generator as oracle/verticut_oracle.c). */
+int vc_index_add_synthetic(vc_index* ix, uint64_t n, uint64_t seed);
+uint64_t vc_synth_word(uint64_t seed, uint64_t id, uint32_t word);
+
+/* Builds all n_tables substring tables (CSR in HBM; occupancy bitmap + rank directory when s = 32).
+ * Replaces the get/append/put loop of load_binarycode (src/build_hash_tables.cc:45-64) and
+ * generate_bitmap (src/generate_bitmap.cc:99-125).  Bucket members end up in ascending id order. */
+int vc_index_build(vc_index* ix);
+
+/* ---- BaseProxy::get -------------------------------------------------------------------- */
+/* get(HashIndex{table,index}, Image_List) (src/base_proxy.h:18, src/search_worker.cc:246): copies up
+ * to `cap` members (ids and/or codes may be NULL) in stored order; *n = bucket size.
+ * Returns VC_OK (found) / VC_NOT_FOUND (empty bucket). */
+int vc_bucket_get(vc_index* ix, uint32_t table, uint32_t index, uint32_t* ids, void* codes, uint32_t cap, uint32_t* n);
+/* get(ID{id}, BinaryCode) (src/linear_search.cc:45-46): VC_OK / VC_NOT_FOUND. */
+int vc_code_get(vc_index* ix, uint32_t id, void* code);
+/* Occupancy bitmap of a table in the reference's layout (bit i of word i/32, src/bitmap.cc:22-38;
+ * one 2^s-bit map per table, src/generate_bitmap.cc:99-125).  n_words = 2^s / 32. */
+int vc_occupancy_bitmap_get(vc_index* ix, uint32_t table, uint32_t* words, uint64_t n_words);
+
+/* ---- search, host buffers (the reference-facing calls) --------------------------------------
+ * queries: nq raw codes.  Outputs are [nq][k]; out_counts[q] <= k results are valid.  Any output
+ * pointer may be NULL. */
+
+/* Brute-force scan: search_K_nearest_neighbors(int k) of src/linear_search.cc:39-64 for a batch. */
+int vc_search_linear(vc_index* ix, const void* queries, uint32_t nq, uint32_t k,
+                     uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts);
+
+/* MIH search: SearchWorker::find (src/search_worker.cc:65-89) for a batch.
+ *  approximate = 0: exact k-NN (search_worker.cc:159-218) with the m-aware strict stop rule
+ *                   d_k <= m*(r+1) - 1 (results identical to vc_search_linear);
+ *  approximate = 1: search_worker.cc:93-157 - stop at the first radius that has seen
+ *                   >= 20*k distinct candidates, return the k best seen;
+ *  max_radius >= 0: fixed-radius mode - search radii 0..max_radius, return the k best seen
+ *                   (overrides both stop rules); max_radius < 0: use the stop rule. */
+int vc_search_mih(vc_index* ix, const void* queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                  uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, vc_query_stats* stats);
+
+/* ---- search, device buffers (multi-GPU plumbing and zero-copy callers) ----------------------
+ * d_queries / d_out_keys live on the index's device; d_out_keys is [nq][k] packed words
+ * (VC_EMPTY_KEY padded), ascending.  `stream` is a cudaStream_t (NULL = default stream); the
+ * call only enqueues work.  d_stats may be NULL. */
+int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, void* stream);
+int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                      uint64_t* d_out_keys, vc_query_stats* d_stats, void* stream);
+
+/* Top-k merge of per-shard results; replaces mpi_coordinator::gather_vectors + the master's heap
+ * (src/mpi_coordinator.cc:34-69, src/search_worker.cc:179-199) for id-disjoint shards.
+ * d_lists is [n_lists][nq][k] (the layout an all-gather of per-GPU [nq][k] results produces);
+ * d_out is [nq][k]. */
+int vc_merge_topk_dev(int device, const uint64_t* d_lists, uint32_t n_lists, uint32_t nq, uint32_t k,
+                      uint64_t* d_out, void* stream);
+/* Host-buffer convenience form of the same merge (copies in, merges on `device`, copies out). */
+int vc_merge_topk(int device, const uint64_t* lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t* out);
+
+/* Tuning / introspection knobs (integers), e.g. "scan.prefilter", "scan.variant", "scan.waves",
+ * "mih.threads".  Unknown names return VC_ERR_ARG.  vc_get_counter reads back launch counts etc. */
+int vc_index_set_param(vc_index* ix, const char* name, int64_t value);
+int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VERTICUT_GPU_H */

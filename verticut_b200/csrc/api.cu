@@ -1,0 +1,707 @@
+// C ABI of libverticut_gpu.so (include/verticut_gpu.h): index object in HBM, build, search, merge.
+// Host code only orchestrates: every byte of the hot path is touched by the kernels in scan.cuh,
+// build.cuh and mih.cuh.  There is no CPU fallback - without a CUDA device the calls fail.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/verticut_gpu.h"
+#include "build.cuh"
+#include "mih.cuh"
+#include "scan.cuh"
+
+using namespace vc;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(e_ == cudaErrorMemoryAllocation ? VC_ERR_NOMEM : VC_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// small RAII helpers
+// ------------------------------------------------------------------------------------------------
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// grow-only device / pinned-host scratch
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return VC_OK;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CU(cudaMalloc(&p, want));
+    cap = want;
+    return VC_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return VC_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    CU(cudaMallocHost(&p, want));
+    cap = want;
+    return VC_OK;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// the index object
+// ------------------------------------------------------------------------------------------------
+struct vc_index {
+  int device = 0;
+  uint32_t bits = 0, W = 0, m = 0, sbits = 0, first_id = 0;
+  uint64_t n = 0, cap = 0;        // codes held / capacity (codes)
+  uint64_t* d_codes = nullptr;    // main table id -> code (src/linear_search.cc:45-46), [cap][W]
+  bool built = false;
+  TableDev tab[kMaxTables];       // host copy of the table descriptors
+  TableDev* d_tab = nullptr;      // device copy
+  uint64_t table_bytes = 0;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  // scratch
+  DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small;
+  PinBuf h_q, h_ids, h_dists, h_counts, h_stats, h_small;
+  // knobs
+  int64_t scan_prefilter = -1;    // -1 auto, 0 off, 1 on
+  int64_t scan_qt = 0;            // 0 auto
+  int64_t scan_waves = 0;         // 0 auto
+  int64_t scan_smem_kb = 0;       // 0 auto: shared memory budget per CTA for the query tile
+  int64_t merge_fanin = 64;
+  // counters
+  int64_t launches = 0;           // kernels launched by this index since creation
+  int64_t last_scan_grid = 0, last_scan_qt = 0, last_scan_slices = 0, last_scan_smem = 0, last_scan_occ = 0;
+};
+
+static void free_tables(vc_index* ix) {
+  for (uint32_t t = 0; t < kMaxTables; ++t) {
+    TableDev& T = ix->tab[t];
+    if (T.row_ptr) cudaFree(T.row_ptr);
+    if (T.bitmap) cudaFree(T.bitmap);
+    if (T.rank_dir) cudaFree(T.rank_dir);
+    if (T.ids) cudaFree(T.ids);
+    if (T.codes) cudaFree(T.codes);
+    memset(&T, 0, sizeof T);
+  }
+  ix->table_bytes = 0;
+  ix->built = false;
+}
+
+static int grid_for(uint64_t n, int threads, int num_sms) {
+  uint64_t blocks = (n + threads - 1) / threads;
+  uint64_t cap = (uint64_t)num_sms * 16;
+  return (int)std::max<uint64_t>(1, std::min(blocks, cap));
+}
+
+extern "C" {
+
+const char* vc_last_error(void) { return g_err.c_str(); }
+int vc_abi_version(void) { return VC_ABI_VERSION; }
+
+int vc_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(VC_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+uint64_t vc_synth_word(uint64_t seed, uint64_t id, uint32_t word) { return synth_word(seed, id, word); }
+
+int vc_index_create(int device, uint32_t code_bits, uint32_t n_tables, uint32_t first_id, vc_index** out) {
+  if (!out) return fail(VC_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (code_bits != 64 && code_bits != 128 && code_bits != 256)
+    return fail(VC_ERR_ARG, "code_bits must be 64, 128 or 256 (got %u)", code_bits);
+  uint32_t sbits = 0;
+  if (n_tables) {
+    if (n_tables > kMaxTables || code_bits % n_tables) return fail(VC_ERR_ARG, "code_bits %u not divisible into %u tables", code_bits, n_tables);
+    sbits = code_bits / n_tables;
+    if (sbits != 8 && sbits != 16 && sbits != 32)
+      return fail(VC_ERR_ARG, "substring width %u unsupported (8, 16 or 32 bits; bucket index is a uint32)", sbits);
+  }
+  int ndev = vc_device_count();
+  if (ndev < 0) return ndev;
+  if (device < 0 || device >= ndev) return fail(VC_ERR_CUDA, "CUDA device %d not available (%d visible)", device, ndev);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(VC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  vc_index* ix = new vc_index();
+  memset(ix->tab, 0, sizeof ix->tab);
+  ix->device = device; ix->bits = code_bits; ix->W = code_bits / 64; ix->m = n_tables; ix->sbits = sbits; ix->first_id = first_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ix; return fail(VC_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+  ix->num_sms = prop.multiProcessorCount;
+  ix->smem_optin = prop.sharedMemPerBlockOptin;
+  // binomial table for the probe enumerator
+  static uint32_t binom[33][33];
+  for (int n = 0; n <= 32; ++n)
+    for (int k = 0; k <= 32; ++k)
+      binom[n][k] = k == 0 ? 1u : (n == 0 ? 0u : (uint32_t)std::min<uint64_t>((uint64_t)binom[n - 1][k - 1] + binom[n - 1][k], 0xFFFFFFFFull));
+  cudaError_t e = cudaMemcpyToSymbol(c_binom, binom, sizeof binom);
+  if (e != cudaSuccess) { delete ix; return fail(VC_ERR_CUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString(e)); }
+  *out = ix;
+  return VC_OK;
+}
+
+void vc_index_destroy(vc_index* ix) {
+  if (!ix) return;
+  DeviceGuard g(ix->device);
+  cudaDeviceSynchronize();
+  free_tables(ix);
+  if (ix->d_tab) cudaFree(ix->d_tab);
+  if (ix->d_codes) cudaFree(ix->d_codes);
+  DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small};
+  for (DevBuf* b : db) b->release();
+  PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
+  for (PinBuf* b : pb) b->release();
+  delete ix;
+}
+
+int vc_index_get_info(const vc_index* ix, vc_index_info* info) {
+  if (!ix || !info) return fail(VC_ERR_ARG, "null argument");
+  info->n_codes = ix->n; info->code_bits = ix->bits; info->n_tables = ix->m; info->substring_bits = ix->sbits;
+  info->first_id = ix->first_id; info->device = ix->device; info->built = ix->built ? 1 : 0;
+  info->device_bytes = ix->cap * ix->W * 8 + ix->table_bytes;
+  return VC_OK;
+}
+
+// capacity is kept a multiple of 4096 codes (+ one 4096 pad) so that 128-bit loads of the last codes stay in bounds
+static int reserve_codes(vc_index* ix, uint64_t total) {
+  if (total > 0xFFFFFFFFull - ix->first_id) return fail(VC_ERR_ARG, "ids would exceed 32 bits (uint32 id, src/image_search.proto:4)");
+  if (total <= ix->cap) return VC_OK;
+  uint64_t want = std::max(total, ix->cap + ix->cap / 2);
+  want = (want + 4095) / 4096 * 4096;
+  uint64_t* nd = nullptr;
+  CU(cudaMalloc(&nd, (want + 4096) * ix->W * 8));
+  if (ix->d_codes) {
+    cudaError_t e = cudaMemcpy(nd, ix->d_codes, ix->n * ix->W * 8, cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) { cudaFree(nd); return fail(VC_ERR_CUDA, "cudaMemcpy D2D: %s", cudaGetErrorString(e)); }
+    cudaFree(ix->d_codes);
+  }
+  ix->d_codes = nd;
+  ix->cap = want;
+  return VC_OK;
+}
+
+int vc_index_add(vc_index* ix, const void* codes, uint64_t n) {
+  if (!ix || (!codes && n)) return fail(VC_ERR_ARG, "null argument");
+  if (n == 0) return VC_OK;
+  DeviceGuard g(ix->device);
+  int rc = reserve_codes(ix, ix->n + n);
+  if (rc) return rc;
+  CU(cudaMemcpy(ix->d_codes + ix->n * ix->W, codes, n * ix->W * 8, cudaMemcpyHostToDevice));
+  ix->n += n;
+  ix->built = false;
+  return VC_OK;
+}
+
+int vc_index_add_device(vc_index* ix, const void* d_codes, uint64_t n) {
+  if (!ix || (!d_codes && n)) return fail(VC_ERR_ARG, "null argument");
+  if (n == 0) return VC_OK;
+  DeviceGuard g(ix->device);
+  int rc = reserve_codes(ix, ix->n + n);
+  if (rc) return rc;
+  CU(cudaMemcpy(ix->d_codes + ix->n * ix->W, d_codes, n * ix->W * 8, cudaMemcpyDeviceToDevice));
+  ix->n += n;
+  ix->built = false;
+  return VC_OK;
+}
+
+int vc_index_add_synthetic(vc_index* ix, uint64_t n, uint64_t seed) {
+  if (!ix) return fail(VC_ERR_ARG, "null argument");
+  if (n == 0) return VC_OK;
+  DeviceGuard g(ix->device);
+  int rc = reserve_codes(ix, ix->n + n);
+  if (rc) return rc;
+  uint64_t* dst = ix->d_codes + ix->n * ix->W;
+  const uint64_t first = (uint64_t)ix->first_id + ix->n;
+  const int grid = grid_for(n * ix->W, 256, ix->num_sms);
+  if (ix->W == 1) synth_codes_kernel<1><<<grid, 256>>>(dst, n, first, seed);
+  else if (ix->W == 2) synth_codes_kernel<2><<<grid, 256>>>(dst, n, first, seed);
+  else synth_codes_kernel<4><<<grid, 256>>>(dst, n, first, seed);
+  ix->launches++;
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  ix->n += n;
+  ix->built = false;
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------------------
+static int exclusive_scan_inplace(vc_index* ix, uint32_t* d, uint64_t n, cudaStream_t st) {
+  // three-phase scan, recursive on block sums; temporary sums are cudaMalloc'ed per level (build-time only)
+  const uint64_t nb = (n + kScanTile - 1) / kScanTile;
+  if (nb <= 1) {
+    scan_apply_kernel<<<1, kBuildThreads, 0, st>>>(d, n, nullptr, d);
+    ix->launches++;
+    CU(cudaGetLastError());
+    return VC_OK;
+  }
+  uint32_t* sums = nullptr;
+  CU(cudaMalloc(&sums, nb * sizeof(uint32_t)));
+  scan_reduce_kernel<<<(unsigned)nb, kBuildThreads, 0, st>>>(d, n, sums);
+  ix->launches++;
+  int rc = exclusive_scan_inplace(ix, sums, nb, st);
+  if (rc == VC_OK) {
+    scan_apply_kernel<<<(unsigned)nb, kBuildThreads, 0, st>>>(d, n, sums, d);
+    ix->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(VC_ERR_CUDA, "scan_apply: %s", cudaGetErrorString(e));
+  }
+  cudaStreamSynchronize(st);
+  cudaFree(sums);
+  return rc;
+}
+
+}  // extern "C"
+
+template <int W>
+static int build_tables_impl(vc_index* ix) {
+  const uint64_t n = ix->n;
+  const uint32_t m = ix->m, sbits = ix->sbits;
+  cudaStream_t st = 0;
+  uint32_t *kA = nullptr, *kB = nullptr, *vA = nullptr, *vB = nullptr, *hist = nullptr;
+  const uint64_t nalloc = std::max<uint64_t>(n, 1);
+  const uint32_t nblocks = (uint32_t)std::max<uint64_t>(1, (n + kSortChunk - 1) / kSortChunk);
+  int rc = VC_OK;
+  auto cleanup = [&]() {
+    if (kA) cudaFree(kA); if (kB) cudaFree(kB); if (vA) cudaFree(vA); if (vB) cudaFree(vB); if (hist) cudaFree(hist);
+  };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(e_ == cudaErrorMemoryAllocation ? VC_ERR_NOMEM : VC_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  CUB(cudaMalloc(&kA, nalloc * 4)); CUB(cudaMalloc(&kB, nalloc * 4));
+  CUB(cudaMalloc(&vA, nalloc * 4)); CUB(cudaMalloc(&vB, nalloc * 4));
+  CUB(cudaMalloc(&hist, (size_t)256 * nblocks * 4));
+  const int g1 = grid_for(nalloc, 256, ix->num_sms);
+  for (uint32_t t = 0; t < m; ++t) {
+    TableDev& T = ix->tab[t];
+    extract_keys_kernel<W><<<g1, 256, 0, st>>>(ix->d_codes, n, t, sbits, kA, vA);
+    ix->launches++;
+    uint32_t *ks = kA, *vs = vA, *kd = kB, *vd = vB;
+    for (uint32_t shift = 0; shift < sbits && n > 0; shift += 8) {
+      radix_hist_kernel<<<nblocks, kBuildThreads, 0, st>>>(ks, n, shift, nblocks, hist);
+      ix->launches++;
+      rc = exclusive_scan_inplace(ix, hist, (uint64_t)256 * nblocks, st);
+      if (rc) { cleanup(); return rc; }
+      radix_scatter_kernel<<<nblocks, kBuildThreads, 0, st>>>(ks, vs, n, shift, nblocks, hist, kd, vd);
+      ix->launches++;
+      std::swap(ks, kd); std::swap(vs, vd);
+    }
+    CUB(cudaGetLastError());
+    // payload
+    CUB(cudaMalloc(&T.ids, (nalloc + 64) * 4));
+    CUB(cudaMalloc(&T.codes, (nalloc + 64) * W * 8));
+    ix->table_bytes += (nalloc + 64) * (4 + W * 8);
+    gather_payload_kernel<W><<<g1, 256, 0, st>>>(ix->d_codes, vs, n, ix->first_id, T.ids, T.codes);
+    ix->launches++;
+    if (sbits <= 16) {
+      const uint64_t nbuckets = 1ull << sbits;
+      T.sparse = 0;
+      CUB(cudaMalloc(&T.row_ptr, (nbuckets + 1) * 4));
+      ix->table_bytes += (nbuckets + 1) * 4;
+      row_ptr_kernel<<<grid_for(n + 1, 256, ix->num_sms), 256, 0, st>>>(ks, n, nbuckets, T.row_ptr);
+      ix->launches++;
+    } else {
+      // s = 32: occupancy bitmap + rank directory + compact starts
+      T.sparse = 1;
+      const uint64_t nwords = 1ull << (sbits - 5);
+      const uint64_t nrb = (1ull << sbits) / kRankBlockBits;
+      CUB(cudaMalloc(&T.bitmap, nwords * 4));
+      CUB(cudaMalloc(&T.rank_dir, nrb * 4));
+      ix->table_bytes += nwords * 4 + nrb * 4;
+      CUB(cudaMemsetAsync(T.bitmap, 0, nwords * 4, st));
+      if (n) { bitmap_set_kernel<<<g1, 256, 0, st>>>(ks, n, T.bitmap); ix->launches++; }
+      bitmap_block_count_kernel<<<grid_for(nrb, 256, ix->num_sms), 256, 0, st>>>(T.bitmap, nrb, T.rank_dir);
+      ix->launches++;
+      uint32_t last_cnt = 0, last_rank = 0;
+      CUB(cudaMemcpyAsync(&last_cnt, T.rank_dir + nrb - 1, 4, cudaMemcpyDeviceToHost, st));
+      CUB(cudaStreamSynchronize(st));
+      rc = exclusive_scan_inplace(ix, T.rank_dir, nrb, st);
+      if (rc) { cleanup(); return rc; }
+      CUB(cudaMemcpyAsync(&last_rank, T.rank_dir + nrb - 1, 4, cudaMemcpyDeviceToHost, st));
+      CUB(cudaStreamSynchronize(st));
+      T.n_unique = last_rank + last_cnt;
+      CUB(cudaMalloc(&T.row_ptr, ((size_t)T.n_unique + 1) * 4));
+      ix->table_bytes += ((size_t)T.n_unique + 1) * 4;
+      sparse_starts_kernel<<<grid_for(n + 1, 256, ix->num_sms), 256, 0, st>>>(ks, n, T.bitmap, T.rank_dir, T.n_unique, T.row_ptr);
+      ix->launches++;
+    }
+    CUB(cudaGetLastError());
+    CUB(cudaStreamSynchronize(st));
+  }
+  cleanup();
+#undef CUB
+  if (!ix->d_tab) CU(cudaMalloc(&ix->d_tab, sizeof(TableDev) * kMaxTables));
+  CU(cudaMemcpy(ix->d_tab, ix->tab, sizeof(TableDev) * kMaxTables, cudaMemcpyHostToDevice));
+  return VC_OK;
+}
+
+extern "C" {
+
+int vc_index_build(vc_index* ix) {
+  if (!ix) return fail(VC_ERR_ARG, "null argument");
+  DeviceGuard g(ix->device);
+  free_tables(ix);
+  if (ix->m == 0) { ix->built = true; return VC_OK; }
+  if (!ix->d_codes) { int rc = reserve_codes(ix, 1); if (rc) return rc; }
+  int rc = ix->W == 1 ? build_tables_impl<1>(ix) : ix->W == 2 ? build_tables_impl<2>(ix) : build_tables_impl<4>(ix);
+  if (rc) { free_tables(ix); return rc; }
+  ix->built = true;
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BaseProxy::get
+// ------------------------------------------------------------------------------------------------
+int vc_bucket_get(vc_index* ix, uint32_t table, uint32_t index, uint32_t* ids, void* codes, uint32_t cap, uint32_t* n_out) {
+  if (!ix || !n_out) return fail(VC_ERR_ARG, "null argument");
+  *n_out = 0;
+  if (!ix->built || ix->m == 0) return fail(VC_ERR_STATE, "tables are not built");
+  if (table >= ix->m) return fail(VC_ERR_ARG, "table %u out of range (%u tables)", table, ix->m);
+  if (ix->sbits < 32 && index >= (1u << ix->sbits)) return VC_NOT_FOUND;
+  DeviceGuard g(ix->device);
+  int rc = ix->d_small.ensure(64);
+  if (rc) return rc;
+  bucket_lookup_kernel<<<1, 1>>>(ix->tab[table], index, (uint32_t*)ix->d_small.p);
+  ix->launches++;
+  uint32_t sl[2];
+  CU(cudaMemcpy(sl, ix->d_small.p, 8, cudaMemcpyDeviceToHost));
+  *n_out = sl[1];
+  if (sl[1] == 0) return VC_NOT_FOUND;
+  const uint32_t ncopy = std::min(cap, sl[1]);
+  if (ids && ncopy) CU(cudaMemcpy(ids, ix->tab[table].ids + sl[0], (size_t)ncopy * 4, cudaMemcpyDeviceToHost));
+  if (codes && ncopy) CU(cudaMemcpy(codes, ix->tab[table].codes + (size_t)sl[0] * ix->W, (size_t)ncopy * ix->W * 8, cudaMemcpyDeviceToHost));
+  return VC_OK;
+}
+
+int vc_code_get(vc_index* ix, uint32_t id, void* code) {
+  if (!ix || !code) return fail(VC_ERR_ARG, "null argument");
+  if (id < ix->first_id || (uint64_t)id - ix->first_id >= ix->n) return VC_NOT_FOUND;
+  DeviceGuard g(ix->device);
+  CU(cudaMemcpy(code, ix->d_codes + (uint64_t)(id - ix->first_id) * ix->W, ix->W * 8, cudaMemcpyDeviceToHost));
+  return VC_OK;
+}
+
+int vc_occupancy_bitmap_get(vc_index* ix, uint32_t table, uint32_t* words, uint64_t n_words) {
+  if (!ix || !words) return fail(VC_ERR_ARG, "null argument");
+  if (!ix->built || ix->m == 0) return fail(VC_ERR_STATE, "tables are not built");
+  if (table >= ix->m) return fail(VC_ERR_ARG, "table %u out of range", table);
+  const uint64_t need = 1ull << (ix->sbits >= 5 ? ix->sbits - 5 : 0);
+  if (ix->sbits < 5 || n_words != need) return fail(VC_ERR_ARG, "bitmap of a %u-bit table has %llu words", ix->sbits, (unsigned long long)need);
+  DeviceGuard g(ix->device);
+  const TableDev& T = ix->tab[table];
+  if (T.sparse) {
+    CU(cudaMemcpy(words, T.bitmap, n_words * 4, cudaMemcpyDeviceToHost));
+  } else {
+    int rc = ix->d_small.ensure(n_words * 4);
+    if (rc) return rc;
+    dense_bitmap_kernel<<<grid_for(n_words, 256, ix->num_sms), 256>>>(T.row_ptr, n_words, (uint32_t*)ix->d_small.p);
+    ix->launches++;
+    CU(cudaMemcpy(words, ix->d_small.p, n_words * 4, cudaMemcpyDeviceToHost));
+  }
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// merge
+// ------------------------------------------------------------------------------------------------
+static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 1; return p; }
+
+// lists [n_lists][nq][k] -> out [nq][k]; uses `scratch` (>= ceil(n_lists/fanin) * nq * k keys) for the tree levels
+static int merge_lists(int64_t* launches, const uint64_t* d_lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t fanin,
+                       uint64_t* d_scratch_a, uint64_t* d_scratch_b, uint64_t* d_out, cudaStream_t st) {
+  const uint32_t BUF = pow2_at_least(k + kMergeThreads);     // <= 4096 entries = 32 KB: no opt-in needed
+  const size_t smem = (size_t)BUF * 8;
+  const uint64_t* in = d_lists;
+  uint32_t nl = n_lists;
+  uint64_t* bufs[2] = {d_scratch_a, d_scratch_b};
+  int flip = 0;
+  while (nl > fanin) {
+    const uint32_t groups = (nl + fanin - 1) / fanin;
+    uint64_t* dst = bufs[flip];
+    merge_topk_kernel<<<dim3(nq, groups), kMergeThreads, smem, st>>>(in, nl, fanin, nq, k, BUF, dst);
+    (*launches)++;
+    in = dst; nl = groups; flip ^= 1;
+  }
+  merge_topk_kernel<<<dim3(nq, 1), kMergeThreads, smem, st>>>(in, nl, nl, nq, k, BUF, d_out);
+  (*launches)++;
+  CU(cudaGetLastError());
+  return VC_OK;
+}
+
+int vc_merge_topk_dev(int device, const uint64_t* d_lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t* d_out, void* stream) {
+  if (!d_lists || !d_out) return fail(VC_ERR_ARG, "null argument");
+  if (k == 0 || k > VC_MAX_K) return fail(VC_ERR_ARG, "k must be in [1, %u]", VC_MAX_K);
+  if (n_lists == 0 || nq == 0) return VC_OK;
+  if (n_lists > 1024) return fail(VC_ERR_ARG, "at most 1024 lists per merge call");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(VC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  int64_t launches = 0;
+  return merge_lists(&launches, d_lists, n_lists, nq, k, 1024, nullptr, nullptr, d_out, (cudaStream_t)stream);
+}
+
+int vc_merge_topk(int device, const uint64_t* lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t* out) {
+  if (!lists || !out) return fail(VC_ERR_ARG, "null argument");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(VC_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  uint64_t *d_in = nullptr, *d_out = nullptr;
+  const size_t nin = (size_t)n_lists * nq * k, nout = (size_t)nq * k;
+  CU(cudaMalloc(&d_in, std::max<size_t>(nin, 1) * 8));
+  cudaError_t e = cudaMalloc(&d_out, std::max<size_t>(nout, 1) * 8);
+  if (e != cudaSuccess) { cudaFree(d_in); return fail(VC_ERR_NOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  cudaMemcpy(d_in, lists, nin * 8, cudaMemcpyHostToDevice);
+  int rc = vc_merge_topk_dev(device, d_in, n_lists, nq, k, d_out, nullptr);
+  if (rc == VC_OK) {
+    e = cudaMemcpy(out, d_out, nout * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail(VC_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_in); cudaFree(d_out);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear scan
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+template <int W, bool PF>
+static int launch_scan(vc_index* ix, const ScanParams& p, size_t smem, cudaStream_t st) {
+  auto kern = scan_topk_kernel<W, PF>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+  kern<<<p.n_qtiles * p.n_slices, kScanThreads, smem, st>>>(p);
+  ix->launches++;
+  CU(cudaGetLastError());
+  return VC_OK;
+}
+
+template <int W, bool PF>
+static int scan_occupancy(size_t smem, int* occ) {
+  CU(cudaFuncSetAttribute(scan_topk_kernel<W, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, scan_topk_kernel<W, PF>, kScanThreads, smem));
+  return VC_OK;
+}
+
+extern "C" {
+
+int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, void* stream) {
+  if (!ix || !d_queries || !d_out_keys) return fail(VC_ERR_ARG, "null argument");
+  if (k == 0 || k > VC_MAX_K) return fail(VC_ERR_ARG, "k must be in [1, %u]", VC_MAX_K);
+  if (nq == 0) return VC_OK;
+  DeviceGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t W = ix->W;
+  const int qstride = W == 1 ? ScanCfg<1>::QSTRIDE : W == 2 ? ScanCfg<2>::QSTRIDE : ScanCfg<4>::QSTRIDE;
+  const uint32_t step = W == 1 ? ScanCfg<1>::STEP : W == 2 ? ScanCfg<2>::STEP : ScanCfg<4>::STEP;
+  ScanParams p;
+  p.codes = (const uint4*)ix->d_codes; p.n = ix->n; p.first_id = ix->first_id;
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k;
+  p.BUF = pow2_at_least(k + kScanThreads);
+  p.compact_at = k + (p.BUF - k) / 2;
+  // query tile: as many queries as fit the shared-memory budget (default: two CTAs per SM)
+  const size_t per_q = scan_smem_bytes(1, p.BUF, qstride) - 16;
+  const size_t budget = ix->scan_smem_kb > 0 ? (size_t)ix->scan_smem_kb * 1024 : (ix->smem_optin > 220 * 1024 ? 110 * 1024 : ix->smem_optin / 2);
+  uint32_t qt = (uint32_t)std::max<size_t>(1, (std::min(budget, ix->smem_optin) - 16) / per_q);
+  if (ix->scan_qt > 0) qt = (uint32_t)ix->scan_qt;
+  qt = std::min(qt, nq);
+  while (scan_smem_bytes(qt, p.BUF, qstride) > ix->smem_optin && qt > 1) --qt;
+  if (scan_smem_bytes(qt, p.BUF, qstride) > ix->smem_optin) return fail(VC_ERR_ARG, "k = %u needs more shared memory than the device has", k);
+  p.QT = qt;
+  p.n_qtiles = (nq + qt - 1) / qt;
+  const size_t smem = scan_smem_bytes(qt, p.BUF, qstride);
+  bool pf = ix->scan_prefilter < 0 ? (W <= 2) : ix->scan_prefilter != 0;
+  int occ = 1, rc;
+  if (W == 1) rc = pf ? scan_occupancy<1, true>(smem, &occ) : scan_occupancy<1, false>(smem, &occ);
+  else if (W == 2) rc = pf ? scan_occupancy<2, true>(smem, &occ) : scan_occupancy<2, false>(smem, &occ);
+  else rc = pf ? scan_occupancy<4, true>(smem, &occ) : scan_occupancy<4, false>(smem, &occ);
+  if (rc) return rc;
+  occ = std::max(occ, 1);
+  const uint64_t capacity = (uint64_t)occ * ix->num_sms;
+  const uint64_t waves = ix->scan_waves > 0 ? (uint64_t)ix->scan_waves : ((uint64_t)p.n_qtiles * 8 <= capacity ? 1 : 8);
+  const uint64_t n_steps = std::max<uint64_t>(1, (ix->n + step - 1) / step);
+  uint64_t slices = std::max<uint64_t>(1, (capacity * waves + p.n_qtiles - 1) / p.n_qtiles);
+  slices = std::min(slices, n_steps);
+  const uint64_t steps_per_slice = (n_steps + slices - 1) / slices;
+  p.slice_codes = steps_per_slice * step;
+  p.n_slices = (uint32_t)((n_steps + steps_per_slice - 1) / steps_per_slice);
+  ix->last_scan_grid = (int64_t)p.n_qtiles * p.n_slices; ix->last_scan_qt = qt; ix->last_scan_slices = p.n_slices;
+  ix->last_scan_smem = (int64_t)smem; ix->last_scan_occ = occ;
+
+  const uint32_t fanin = (uint32_t)std::max<int64_t>(2, ix->merge_fanin);
+  const size_t part_keys = (size_t)p.n_slices * nq * k;
+  rc = ix->d_partial.ensure(part_keys * 8);
+  if (rc) return rc;
+  p.partial = (uint64_t*)ix->d_partial.p;
+  uint64_t *sa = nullptr, *sb = nullptr;
+  if (p.n_slices > fanin) {
+    const size_t lvl1 = (size_t)((p.n_slices + fanin - 1) / fanin) * nq * k;
+    const size_t lvl2 = (size_t)((lvl1 / ((size_t)nq * k) + fanin - 1) / fanin) * nq * k;
+    rc = ix->d_partial2.ensure((lvl1 + lvl2) * 8);
+    if (rc) return rc;
+    sa = (uint64_t*)ix->d_partial2.p; sb = sa + lvl1;
+  }
+  if (W == 1) rc = pf ? launch_scan<1, true>(ix, p, smem, st) : launch_scan<1, false>(ix, p, smem, st);
+  else if (W == 2) rc = pf ? launch_scan<2, true>(ix, p, smem, st) : launch_scan<2, false>(ix, p, smem, st);
+  else rc = pf ? launch_scan<4, true>(ix, p, smem, st) : launch_scan<4, false>(ix, p, smem, st);
+  if (rc) return rc;
+  return merge_lists(&ix->launches, p.partial, p.n_slices, nq, k, fanin, sa, sb, d_out_keys, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MIH
+// ------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+template <int W, bool APPROX>
+static int launch_mih(vc_index* ix, const MihParams& p, cudaStream_t st) {
+  auto kern = mih_search_kernel<W, APPROX>;
+  const size_t smem = (size_t)p.BUFM * 8 + (size_t)kMihWarps * kMihWbuf * 8;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  kern<<<p.nq, kMihThreads, smem, st>>>(p);
+  ix->launches++;
+  CU(cudaGetLastError());
+  return VC_OK;
+}
+
+extern "C" {
+
+int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                      uint64_t* d_out_keys, vc_query_stats* d_stats, void* stream) {
+  if (!ix || !d_queries || !d_out_keys) return fail(VC_ERR_ARG, "null argument");
+  if (k == 0 || k > VC_MAX_K) return fail(VC_ERR_ARG, "k must be in [1, %u]", VC_MAX_K);
+  if (ix->m == 0) return fail(VC_ERR_STATE, "index was created without tables (n_tables = 0)");
+  if (!ix->built) return fail(VC_ERR_STATE, "tables are not built (call vc_index_build after adding codes)");
+  if (nq == 0) return VC_OK;
+  DeviceGuard g(ix->device);
+  MihParams p;
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = ix->m; p.sbits = ix->sbits;
+  p.BUFM = pow2_at_least(k + kMihWbuf);
+  p.approximate = approximate; p.max_radius = max_radius;
+  p.tables = ix->d_tab; p.out_keys = d_out_keys; p.stats = d_stats;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool ap = approximate != 0 && max_radius < 0;
+  if (ix->W == 1) return ap ? launch_mih<1, true>(ix, p, st) : launch_mih<1, false>(ix, p, st);
+  if (ix->W == 2) return ap ? launch_mih<2, true>(ix, p, st) : launch_mih<2, false>(ix, p, st);
+  return ap ? launch_mih<4, true>(ix, p, st) : launch_mih<4, false>(ix, p, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer search entry points: H2D queries, search, unpack, D2H results
+// ------------------------------------------------------------------------------------------------
+static int search_host(vc_index* ix, bool mih, const void* queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                       uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, vc_query_stats* stats) {
+  if (!ix || (!queries && nq)) return fail(VC_ERR_ARG, "null argument");
+  if (k == 0 || k > VC_MAX_K) return fail(VC_ERR_ARG, "k must be in [1, %u]", VC_MAX_K);
+  if (nq == 0) return VC_OK;
+  DeviceGuard g(ix->device);
+  const size_t qbytes = (size_t)nq * ix->W * 8, rk = (size_t)nq * k;
+  int rc;
+  if ((rc = ix->d_q.ensure(qbytes)) || (rc = ix->h_q.ensure(qbytes)) || (rc = ix->d_keys.ensure(rk * 8)) ||
+      (rc = ix->d_ids.ensure(rk * 4)) || (rc = ix->d_dists.ensure(rk * 4)) || (rc = ix->d_counts.ensure((size_t)nq * 4)) ||
+      (rc = ix->h_ids.ensure(rk * 4)) || (rc = ix->h_dists.ensure(rk * 4)) || (rc = ix->h_counts.ensure((size_t)nq * 4)))
+    return rc;
+  if (stats && ((rc = ix->d_stats.ensure((size_t)nq * sizeof(vc_query_stats))) || (rc = ix->h_stats.ensure((size_t)nq * sizeof(vc_query_stats)))))
+    return rc;
+  cudaStream_t st = 0;
+  memcpy(ix->h_q.p, queries, qbytes);
+  CU(cudaMemcpyAsync(ix->d_q.p, ix->h_q.p, qbytes, cudaMemcpyHostToDevice, st));
+  if (mih) rc = vc_search_mih_dev(ix, ix->d_q.p, nq, k, approximate, max_radius, (uint64_t*)ix->d_keys.p,
+                                  stats ? (vc_query_stats*)ix->d_stats.p : nullptr, st);
+  else rc = vc_search_linear_dev(ix, ix->d_q.p, nq, k, (uint64_t*)ix->d_keys.p, st);
+  if (rc) return rc;
+  unpack_keys_kernel<<<nq, 128, 0, st>>>((const uint64_t*)ix->d_keys.p, nq, k, (uint32_t*)ix->d_ids.p, (uint32_t*)ix->d_dists.p,
+                                         (uint32_t*)ix->d_counts.p);
+  ix->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ix->h_ids.p, ix->d_ids.p, rk * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ix->h_dists.p, ix->d_dists.p, rk * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ix->h_counts.p, ix->d_counts.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  if (stats) CU(cudaMemcpyAsync(ix->h_stats.p, ix->d_stats.p, (size_t)nq * sizeof(vc_query_stats), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (out_ids) memcpy(out_ids, ix->h_ids.p, rk * 4);
+  if (out_dists) memcpy(out_dists, ix->h_dists.p, rk * 4);
+  if (out_counts) memcpy(out_counts, ix->h_counts.p, (size_t)nq * 4);
+  if (stats) memcpy(stats, ix->h_stats.p, (size_t)nq * sizeof(vc_query_stats));
+  return VC_OK;
+}
+
+int vc_search_linear(vc_index* ix, const void* queries, uint32_t nq, uint32_t k, uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts) {
+  return search_host(ix, false, queries, nq, k, 0, -1, out_ids, out_dists, out_counts, nullptr);
+}
+
+int vc_search_mih(vc_index* ix, const void* queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                  uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, vc_query_stats* stats) {
+  return search_host(ix, true, queries, nq, k, approximate, max_radius, out_ids, out_dists, out_counts, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// knobs
+// ------------------------------------------------------------------------------------------------
+int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
+  if (!ix || !name) return fail(VC_ERR_ARG, "null argument");
+  if (!strcmp(name, "scan.prefilter")) ix->scan_prefilter = value;
+  else if (!strcmp(name, "scan.qt")) ix->scan_qt = value;
+  else if (!strcmp(name, "scan.waves")) ix->scan_waves = value;
+  else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
+  else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
+  else return fail(VC_ERR_ARG, "unknown parameter '%s'", name);
+  return VC_OK;
+}
+
+int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
+  if (!ix || !name || !value) return fail(VC_ERR_ARG, "null argument");
+  if (!strcmp(name, "scan.prefilter")) *value = ix->scan_prefilter;
+  else if (!strcmp(name, "scan.qt")) *value = ix->scan_qt;
+  else if (!strcmp(name, "scan.waves")) *value = ix->scan_waves;
+  else if (!strcmp(name, "scan.smem_kb")) *value = ix->scan_smem_kb;
+  else if (!strcmp(name, "merge.fanin")) *value = ix->merge_fanin;
+  else if (!strcmp(name, "launches")) *value = ix->launches;
+  else if (!strcmp(name, "scan.last_grid")) *value = ix->last_scan_grid;
+  else if (!strcmp(name, "scan.last_qt")) *value = ix->last_scan_qt;
+  else if (!strcmp(name, "scan.last_slices")) *value = ix->last_scan_slices;
+  else if (!strcmp(name, "scan.last_smem")) *value = ix->last_scan_smem;
+  else if (!strcmp(name, "scan.last_occ")) *value = ix->last_scan_occ;
+  else if (!strcmp(name, "num_sms")) *value = ix->num_sms;
+  else return fail(VC_ERR_ARG, "unknown parameter '%s'", name);
+  return VC_OK;
+}
+
+}  // extern "C"

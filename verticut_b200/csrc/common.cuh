@@ -1,0 +1,115 @@
+// Shared device helpers of the verticut_b200 kernels (sm_100a).
+//
+//  - packed result word  (dist << 32 | id)           src/search_worker.cc:12-13,254-256
+//  - Hamming distance    XOR + POPC                   Pilaf/image_tools.h:21-33
+//  - TopK buffer in shared memory with warp / block bitonic compaction; replaces the
+//    std::priority_queue of src/search_worker.cc:160,192-197 and src/linear_search.cc:43,51-56
+//    with the canonical tie rule (ascending packed word = ascending (dist, id)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vc {
+
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kInfDist = 0x7FFFFFFFu;   // "no threshold yet"
+
+__host__ __device__ __forceinline__ uint64_t pack_key(uint32_t dist, uint32_t id) {
+  return ((uint64_t)dist << 32) | id;
+}
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (each code is used once per CTA).
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---------------------------------------------------------------------------------------------
+// Bitonic sort of P (power of two) u64 keys in shared memory by `nthreads` cooperating threads
+// (tid in [0, nthreads)).  SYNC() must synchronise exactly those threads.
+// ---------------------------------------------------------------------------------------------
+template <class SyncFn>
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, uint32_t P, uint32_t tid, uint32_t nthreads, SyncFn sync) {
+  for (uint32_t k2 = 2; k2 <= P; k2 <<= 1) {
+    for (uint32_t j = k2 >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = tid; t < (P >> 1); t += nthreads) {
+        uint32_t l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        uint32_t r = l | j;
+        bool asc = (l & k2) == 0;
+        uint64_t x = a[l], y = a[r];
+        if ((x > y) == asc) { a[l] = y; a[r] = x; }
+      }
+      sync();
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t v) {
+  return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// One query's candidate buffer: `buf` holds `*cnt` unsorted packed words (cnt may have run past
+// `cap` if appends overflowed; those were dropped by the caller).  compact() sorts, keeps the k
+// smallest, and returns the new threshold: the k-th smallest word when the buffer holds k, else
+// kEmptyKey (everything passes).  Executed by one warp (all 32 lanes) or by a whole block.
+// ---------------------------------------------------------------------------------------------
+template <class SyncFn>
+__device__ __forceinline__ uint64_t topk_compact(uint64_t* buf, uint32_t* cnt, uint32_t cap, uint32_t k,
+                                                 uint32_t tid, uint32_t nthreads, SyncFn sync) {
+  uint32_t n = min(*cnt, cap);
+  uint32_t P = max(next_pow2(n), 2u);
+  for (uint32_t i = n + tid; i < P; i += nthreads) buf[i] = kEmptyKey;
+  sync();
+  bitonic_sort_smem(buf, P, tid, nthreads, sync);
+  uint32_t kept = min(n, k);
+  uint64_t tau = (kept == k) ? buf[k - 1] : kEmptyKey;
+  sync();
+  if (tid == 0) *cnt = kept;
+  sync();
+  return tau;
+}
+
+struct WarpSync  { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
+struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+
+// Hamming distance helpers on 64-bit words held as two 32-bit halves.
+template <int W> struct CodeRegs { uint32_t w[2 * W]; };   // W 64-bit words = 2W 32-bit words
+
+template <int W>
+__device__ __forceinline__ uint32_t hamming_exact(const uint32_t* __restrict__ c, const uint32_t* __restrict__ q) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 2 * W; ++i) d += __popc(c[i] ^ q[i]);
+  return d;
+}
+// Lower bound of the distance with half the POPCs: popc(x | y) <= popc(x) + popc(y).
+template <int W>
+__device__ __forceinline__ uint32_t hamming_lower_bound(const uint32_t* __restrict__ c, const uint32_t* __restrict__ q) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) d += __popc((c[2 * i] ^ q[2 * i]) | (c[2 * i + 1] ^ q[2 * i + 1]));
+  return d;
+}
+
+// splitmix64-based synthetic code words (must match oracle/verticut_oracle.c: vo_synth_word)
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t synth_word(uint64_t seed, uint64_t id, uint32_t word) {
+  return splitmix64(splitmix64(seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(word + 1))) + id);
+}
+
+}  // namespace vc
