@@ -1,0 +1,178 @@
+"""GPU parity, index build (K1/K8) and MIH search (K2-K5) through the C ABI vs the CPU oracle.
+Contracts: P2 exact MIH == linear scan == canonical oracle, exactly; P4 radius / probe
+statistics; build: every bucket has the oracle's members in ascending id order."""
+import numpy as np
+import pytest
+
+from verticut_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(oracle, n, bits, m, first_id=0, seed=12345):
+    nbytes = bits // 8
+    codes = oracle.synth_codes(seed, first_id, n, nbytes)
+    ix = capi.Index(bits, m, first_id=first_id)
+    ix.add(codes)
+    ix.build()
+    return codes, ix
+
+
+@pytest.mark.parametrize("bits,m", [(64, 4), (64, 8), (128, 8), (64, 2), (128, 4), (256, 16)])
+def test_build_buckets_match_oracle(oracle, bits, m):
+    n = 20_000
+    codes, ix = _mk(oracle, n, bits, m)
+    oix = oracle.Index(codes, m)
+    sbits = bits // m
+    rng = np.random.default_rng(1)
+    for t in range(m):
+        # buckets of real codes (non-empty) plus random keys (mostly empty when s = 32)
+        keys = [oracle.binary_to_int(codes[i, t * sbits // 8:(t + 1) * sbits // 8]) for i in rng.integers(0, n, 6)]
+        keys += [int(x) for x in rng.integers(0, 1 << sbits, 6)]
+        for key in keys:
+            orc, oids = oix.bucket(t, key)
+            rc, ids, bcodes = ix.bucket_get(t, key)
+            assert rc == orc
+            np.testing.assert_array_equal(ids, oids)
+            if ids.size:
+                assert (np.diff(ids.astype(np.int64)) > 0).all()          # ascending id = insertion order
+                np.testing.assert_array_equal(bcodes, codes[ids])
+    ix.close()
+
+
+def test_build_integrity_every_code_in_its_bucket(oracle):
+    # the check of the reference's integrity_check.cc:25-35,52-67, through BaseProxy::get
+    n, bits, m = 3000, 64, 4
+    codes, ix = _mk(oracle, n, bits, m, first_id=100)
+    for t in range(m):
+        for i in range(0, n, 37):
+            key = oracle.binary_to_int(codes[i, 2 * t:2 * t + 2])
+            rc, ids, bcodes = ix.bucket_get(t, key)
+            assert rc == 0
+            j = np.nonzero(ids == 100 + i)[0]
+            assert j.size == 1 and (bcodes[j[0]] == codes[i]).all()
+    rc, code = ix.code_get(100 + 5)
+    assert rc == 0 and (code == codes[5]).all()
+    assert ix.code_get(99)[0] == 1 and ix.code_get(100 + n)[0] == 1
+    ix.close()
+
+
+@pytest.mark.parametrize("bits,m", [(64, 4), (128, 8)])
+def test_occupancy_bitmap_matches_oracle(oracle, bits, m):
+    codes, ix = _mk(oracle, 30_000, bits, m)
+    oix = oracle.Index(codes, m)
+    for t in (0, m - 1):
+        np.testing.assert_array_equal(ix.occupancy_bitmap(t), oix.occupancy_bitmap(t))
+    ix.close()
+
+
+def _check_exact(oracle, n, bits, m, nq, k, first_id=0):
+    codes, ix = _mk(oracle, n, bits, m, first_id=first_id)
+    queries = oracle.synth_codes(67890, 0, nq, bits // 8)
+    ids, dists, counts, stats = ix.search_mih(queries, k)
+    lid, ld, lc = oracle.linear_search(codes, queries, k, first_id=first_id)
+    np.testing.assert_array_equal(counts, lc)
+    np.testing.assert_array_equal(dists, ld)
+    np.testing.assert_array_equal(ids, lid)
+    gid, gd, gc = ix.search_linear(queries, k)
+    np.testing.assert_array_equal(gid, ids)
+    np.testing.assert_array_equal(gd, dists)
+    # statistics against the canonical oracle MIH (strict m-aware stop rule)
+    oix = oracle.Index(codes, m, first_id=first_id)
+    oid, od, oc, ost = oix.search(queries, k, order=oracle.ORDER_CANONICAL, stop=oracle.STOP_STRICT_M)
+    np.testing.assert_array_equal(oid, ids)
+    for q in range(nq):
+        assert stats["radius"][q] == ost[q]["radius"]
+        assert stats["candidates"][q] == ost[q]["candidates"]
+        if bits // m < 32:
+            assert stats["probes"][q] == ost[q]["probes"]
+        else:
+            assert stats["occupancy_tests"][q] == ost[q]["probes"]
+        assert stats["n_results"][q] == counts[q]
+    ix.close()
+
+
+@pytest.mark.parametrize("n,bits,m,nq,k", [
+    (20_000, 64, 4, 16, 10),
+    (200_000, 64, 4, 8, 100),
+    (50_000, 128, 8, 6, 100),
+    (20_000, 64, 8, 5, 10),
+    (3_000, 64, 2, 4, 10),       # s = 32: bitmap + rank directory tables
+    (5_000, 256, 16, 3, 50),
+])
+def test_mih_exact_equals_linear_scan(oracle, n, bits, m, nq, k):
+    _check_exact(oracle, n, bits, m, nq, k)
+
+
+def test_mih_first_id_offset(oracle):
+    _check_exact(oracle, 30_000, 64, 4, 5, 100, first_id=3_000_000_000)
+
+
+def test_mih_fewer_codes_than_k(oracle):
+    _check_exact(oracle, 50, 64, 4, 3, 100)
+
+
+def test_mih_large_k(oracle):
+    _check_exact(oracle, 20_000, 64, 4, 2, 1000)
+
+
+def test_mih_heavy_ties(oracle):
+    n, k = 5000, 100
+    base = oracle.synth_codes(9, 0, 4, 8)
+    codes = np.repeat(base, n // 4, axis=0)                # four distinct codes, 1250 copies each
+    ix = capi.Index(64, 4)
+    ix.add(codes)
+    ix.build()
+    queries = oracle.synth_codes(67890, 0, 6, 8)
+    queries[0] = base[2]
+    ids, dists, counts, _ = ix.search_mih(queries, k)
+    lid, ld, lc = oracle.linear_search(codes, queries, k)
+    np.testing.assert_array_equal(ids, lid)
+    np.testing.assert_array_equal(dists, ld)
+    ix.close()
+
+
+@pytest.mark.parametrize("bits,m,r", [(64, 4, 0), (64, 4, 2), (128, 8, 1), (256, 16, 1), (256, 8, 2)])
+def test_mih_fixed_radius(oracle, bits, m, r):
+    n, nq, k = 30_000, 4, 100
+    codes, ix = _mk(oracle, n, bits, m)
+    queries = codes[:nq].copy()
+    queries[:, 0] ^= 1                                      # near-duplicates so that small radii find something
+    ids, dists, counts, stats = ix.search_mih(queries, k, max_radius=r)
+    oix = oracle.Index(codes, m)
+    oid, od, oc, ost = oix.search(queries, k, max_radius=r)
+    np.testing.assert_array_equal(counts, oc)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    assert (stats["radius"] == r).all()
+    ix.close()
+
+
+@pytest.mark.parametrize("bits,m,k", [(64, 4, 10), (128, 8, 3)])
+def test_mih_approximate(oracle, bits, m, k):
+    n, nq = 40_000, 6
+    codes, ix = _mk(oracle, n, bits, m)
+    queries = oracle.synth_codes(67890, 0, nq, bits // 8)
+    ids, dists, counts, stats = ix.search_mih(queries, k, approximate=True)
+    oix = oracle.Index(codes, m)
+    oid, od, oc, ost = oix.search(queries, k, approximate=True)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    for q in range(nq):
+        assert stats["radius"][q] == ost[q]["radius"]
+        assert stats["unique"][q] == ost[q]["unique"]
+    ix.close()
+
+
+def test_mih_errors():
+    ix = capi.Index(64, 4)
+    with pytest.raises(capi.VerticutError):
+        ix.search_mih(np.zeros((1, 8), np.uint8), 10)      # not built
+    ix.build()
+    with pytest.raises(capi.VerticutError):
+        ix.search_mih(np.zeros((1, 8), np.uint8), 0)
+    with pytest.raises(capi.VerticutError):
+        capi.Index(64, 3)
+    with pytest.raises(capi.VerticutError):
+        capi.Index(96, 4)
+    ix.close()
