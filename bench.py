@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of verticut_b200 (see BASELINE.json).
+
+Metric : exact k-NN queries/s at k = 100 over 1 B 64-bit codes (uniform synthetic), database sharded by id
+         over the N GPUs of one box (strong scaling: total work fixed), plus scan HBM GB/s vs peak.
+Step   : one batch of Q queries answered exactly by the MIH path (m = 4 tables) on every shard, followed
+         (N > 1) by one NCCL all-gather of the local top-k and the merge kernel.
+value  : whole-job queries/s with the query batch already resident in HBM.
+e2e    : the same through the host-buffer call (vc_search_mih, pinned staging, H2D + D2H inside the timed region).
+roofline: dominant kernel (mih_search_kernel) - algorithmic bytes / CUDA-event time,
+         against the measured HBM peak of MEASURED_PEAKS.json.
+scan   : the brute-force path (config C4): passes/s at small batches as HBM GB/s vs peak, queries/s at a large batch.
+cpu_baseline: the reference's own linear scan (oracle/_ref, unmodified sources) on a bounded sample, host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+Environment overrides for quick runs: VC_BENCH_N (total codes), VC_BENCH_Q (batch), VC_BENCH_MODE (mih|linear).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K_NN = 100
+CODE_BITS = 64
+N_TABLES = 4
+DB_SEED, QUERY_SEED = 12345, 67890
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_queries(seed, nq, nbytes):
+    rng = np.random.default_rng(seed)
+    return rng.integers(0, 256, size=(nq, nbytes), dtype=np.uint8)
+
+
+def reference_arm(args, n_total, world, rank):
+    """--impl reference: the reference's own CPU linear scan (oracle/_ref) on a bounded sample."""
+    if rank != 0:
+        return
+    from oracle import reference as ref, restatement as R
+    cores = os.cpu_count() or 1
+    sample_n = int(os.environ.get("VC_BENCH_REF_N", 16_000_000))
+    nq = max(cores, 8)
+    codes = R.synth_codes(DB_SEED, 0, sample_n, CODE_BITS // 8)
+    mem = ref.RefMem(codes, 0)
+    times = []
+    for step in range(args.warmup + args.steps):
+        q = make_queries(QUERY_SEED + step, nq, CODE_BITS // 8)
+        t0 = time.perf_counter()
+        mem.linear_search(q, K_NN, n_procs=cores)
+        dt = time.perf_counter() - t0
+        if step >= args.warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    qps_sample = nq / per_step
+    qps = qps_sample * sample_n / n_total          # the scan is linear in N
+    line = {
+        "impl": "reference", "metric": "queries/sec (k=100, 1B 64-bit codes)", "value": qps, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 xor+popcount", "data": "synthetic",
+        "config": {"workload": "exact k-NN, k=100, %d x 64-bit uniform codes" % n_total},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "reference",
+                         "sample": "reference src/linear_search.cc:39-64 (unmodified, oracle/_ref) over an in-memory "
+                                   "%d-code sample, %d queries/step on %d forked processes; scaled by sample/N (scan is linear in N)"
+                                   % (sample_n, nq, cores)},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_total = int(os.environ.get("VC_BENCH_N", 1_000_000_000))
+    Q = int(os.environ.get("VC_BENCH_Q", 1024))
+    mode = os.environ.get("VC_BENCH_MODE", "mih")
+    nbytes = CODE_BITS // 8
+
+    if args.impl == "reference":
+        reference_arm(args, n_total, world, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from verticut_b200 import capi
+    from verticut_b200.sharded import ShardedSearcher, shard_range
+
+    if not torch.cuda.is_available() or capi.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak_gbs, peak_src = measured_peaks()
+
+    # ---- this rank's shard: synthetic codes generated on the device, all m tables built in HBM --------
+    b, e = shard_range(n_total, world, rank)
+    t0 = time.perf_counter()
+    ix = capi.Index(CODE_BITS, N_TABLES, device=local_rank, first_id=b)
+    ix.add_synthetic(e - b, DB_SEED)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ix.build()
+    t_build = time.perf_counter() - t0
+    ix.set_param("profile", 1)
+    searcher = ShardedSearcher(ix)
+
+    n_batches = args.warmup + args.steps
+    host_batches = [make_queries(QUERY_SEED + i, Q, nbytes) for i in range(n_batches)]
+    pinned = [torch.from_numpy(hb).pin_memory() for hb in host_batches]
+    dev_batches = [p.to(dev) for p in pinned]
+    torch.cuda.synchronize()
+
+    def step(i):
+        return searcher.search(dev_batches[i], K_NN, mode=mode)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    launches0 = ix.get_param("launches")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ns = []
+    barrier()
+    ev0.record()
+    for i in range(args.warmup, n_batches):
+        step(i)
+        kernel_ns.append(ix.get_param("last_kernel_ns"))
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = ix.get_param("launches") - launches0 + (0 if world == 1 else 0)
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = Q / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel: algorithmic bytes from the kernel's own statistics ------------
+    stats_t = torch.zeros((Q, capi.STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    keys_t = torch.empty((Q, K_NN), dtype=torch.int64, device=dev)
+    roofline = None
+    if mode == "mih":
+        ix.search_mih_dev(dev_batches[-1].data_ptr(), Q, K_NN, keys_t.data_ptr(), d_stats=stats_t.data_ptr(),
+                          stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        st = stats_t.cpu().numpy().view(capi.STATS_DTYPE).reshape(-1)
+        probes, cands = float(st["probes"].sum()), float(st["candidates"].sum())
+        algo_bytes = probes * 8 + cands * nbytes          # two 4-byte row_ptr reads per probe + the candidates' codes
+        k_s = float(np.mean(kernel_ns)) * 1e-9
+        achieved = algo_bytes / k_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "mih_search_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_s * 1e3,
+                    "probes_per_query": probes / Q, "candidates_per_query": cands / Q,
+                    "mean_radius": float(st["radius"].mean()),
+                    "survey_formula_GBps": (probes * 8 + cands * (4 + nbytes)) / k_s / 1e9}
+
+    # ---- e2e: host buffers through the C ABI (N = 1) or pinned -> device -> search -> merged -> host (N > 1) ----
+    e2e_steps = max(3, min(args.steps, 5))
+    out_host = torch.empty((Q, K_NN), dtype=torch.int64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        hb = host_batches[(args.warmup + i) % n_batches]
+        if world == 1 and mode == "mih":
+            ix.search_mih(hb, K_NN, with_stats=False)
+        elif world == 1:
+            ix.search_linear(hb, K_NN)
+        else:
+            dq = pinned[(args.warmup + i) % n_batches].to(dev, non_blocking=True)
+            res = searcher.search(dq, K_NN, mode=mode)
+            out_host.copy_(res, non_blocking=True)
+            torch.cuda.synchronize()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = {"value": Q / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": Q * nbytes,
+           "d2h_bytes_per_step": Q * K_NN * 8 + (Q * 4 if world == 1 else 0)}
+
+    # ---- the brute-force scan (config C4) on the same shard: HBM-bound at small batches ---------------------
+    scan = {}
+    shard_bytes = (e - b) * nbytes
+    for B in (1, 2, 4, 1024):
+        if B > 8 and os.environ.get("VC_BENCH_SKIP_BIG_SCAN"):
+            continue
+        qd = dev_batches[0][:B].contiguous()
+        reps = 5 if B <= 8 else 1
+        for _ in range(2 if B <= 8 else 1):
+            searcher.search(qd, K_NN, mode="linear")
+        barrier()
+        ks = []
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(reps):
+            searcher.search(qd, K_NN, mode="linear")
+            ks.append(ix.get_param("last_kernel_ns"))
+        s1.record()
+        barrier()
+        ms = s0.elapsed_time(s1) / reps
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        k_ms = float(np.mean(ks)) * 1e-6
+        scan["B=%d" % B] = {"queries_per_s": B / (ms * 1e-3), "ms_per_batch": ms, "scan_kernel_ms": k_ms,
+                            "hbm_GBps_per_gpu": shard_bytes / (k_ms * 1e-3) / 1e9,
+                            "frac_of_peak": shard_bytes / (k_ms * 1e-3) / 1e9 / peak_gbs,
+                            "pair_rate_T_per_s": B * (e - b) / (k_ms * 1e-3) / 1e12}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own linear scan on a bounded sample -----
+    cpu_baseline = None
+    if world == 1 and rank == 0 and not os.environ.get("VC_BENCH_SKIP_CPU"):
+        try:
+            from oracle import reference as ref, restatement as R
+            cores = os.cpu_count() or 1
+            sample_n = int(os.environ.get("VC_BENCH_REF_N", 16_000_000))
+            nq_cpu = max(cores, 8)
+            codes = R.synth_codes(DB_SEED, 0, sample_n, nbytes)
+            mem = ref.RefMem(codes, 0)
+            qh = make_queries(QUERY_SEED, nq_cpu, nbytes)
+            t0 = time.perf_counter()
+            mem.linear_search(qh, K_NN, n_procs=cores)
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": nq_cpu / dt * sample_n / n_total, "unit": "queries/s", "cores": cores, "kind": "reference",
+                            "sample": "reference src/linear_search.cc:39-64 (unmodified, oracle/_ref) over an in-memory %d-code "
+                                      "sample, %d queries on %d forked processes, %.1f s; scaled by sample/N (scan is linear in N)"
+                                      % (sample_n, nq_cpu, cores, dt)}
+        except Exception as ex:   # the checker library did not travel / build
+            cpu_baseline = {"value": None, "unit": "queries/s", "cores": os.cpu_count(), "kind": "reference",
+                            "sample": "unavailable: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": "queries/sec (k=100, 1B 64-bit codes)", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64 xor+popcount", "data": "synthetic",
+            "config": {"workload": "exact k-NN (MIH m=%d, strict stop rule) k=%d over %d x %d-bit uniform codes, batch %d, "
+                                   "id-sharded over %d GPU(s)" % (N_TABLES, K_NN, n_total, CODE_BITS, Q, world)
+                       if mode == "mih" else "exact k-NN (linear scan) k=%d over %d x %d-bit codes, batch %d" % (K_NN, n_total, CODE_BITS, Q),
+                       "mode": mode, "batch": Q, "n_codes": n_total, "codes_per_gpu": e - b,
+                       "l2": "inputs larger than L2 (tables %.1f GB per GPU, >= 300 MB touched per query)" % (ix.info()["device_bytes"] / 1e9),
+                       "parallelism": "id-shard x%d, NCCL all-gather top-k merge" % world},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
+        }
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -99,17 +99,24 @@ struct vc_index {
   int num_sms = 0;
   size_t smem_optin = 0;
   // scratch
-  DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small;
+  DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small, d_gstate;
   PinBuf h_q, h_ids, h_dists, h_counts, h_stats, h_small;
   // knobs
   int64_t scan_prefilter = -1;    // -1 auto, 0 off, 1 on
   int64_t scan_qt = 0;            // 0 auto
   int64_t scan_waves = 0;         // 0 auto
+  int64_t scan_stages = 0;        // 0 auto: ring depth
+  int64_t scan_ctas_per_sm = 2;    // shared-memory plan targets this many resident CTAs per SM
+  int64_t scan_interleave = 1;    // slices interleaved step-wise (1) or contiguous (0)
   int64_t scan_smem_kb = 0;       // 0 auto: shared memory budget per CTA for the query tile
   int64_t merge_fanin = 64;
+  // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
+  int64_t profile = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
   // counters
   int64_t launches = 0;           // kernels launched by this index since creation
-  int64_t last_scan_grid = 0, last_scan_qt = 0, last_scan_slices = 0, last_scan_smem = 0, last_scan_occ = 0;
+  int64_t last_scan_grid = 0, last_scan_qt = 0, last_scan_slices = 0, last_scan_smem = 0, last_scan_occ = 0, last_scan_stages = 0;
 };
 
 static void free_tables(vc_index* ix) {
@@ -188,7 +195,8 @@ void vc_index_destroy(vc_index* ix) {
   free_tables(ix);
   if (ix->d_tab) cudaFree(ix->d_tab);
   if (ix->d_codes) cudaFree(ix->d_codes);
-  DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small};
+  if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
+  DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
   for (PinBuf* b : pb) b->release();
@@ -507,7 +515,9 @@ template <int W, bool PF>
 static int launch_scan(vc_index* ix, const ScanParams& p, size_t smem, cudaStream_t st) {
   auto kern = scan_topk_kernel<W, PF>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-  kern<<<p.n_qtiles * p.n_slices, kScanThreads, smem, st>>>(p);
+  if (ix->profile) cudaEventRecord(ix->ev0, st);
+  kern<<<p.n_qtiles * p.n_slices, kScanCtaThreads, smem, st>>>(p);
+  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; }
   ix->launches++;
   CU(cudaGetLastError());
   return VC_OK;
@@ -516,7 +526,7 @@ static int launch_scan(vc_index* ix, const ScanParams& p, size_t smem, cudaStrea
 template <int W, bool PF>
 static int scan_occupancy(size_t smem, int* occ) {
   CU(cudaFuncSetAttribute(scan_topk_kernel<W, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, scan_topk_kernel<W, PF>, kScanThreads, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, scan_topk_kernel<W, PF>, kScanCtaThreads, smem));
   return VC_OK;
 }
 
@@ -530,24 +540,34 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   cudaStream_t st = (cudaStream_t)stream;
   const uint32_t W = ix->W;
   const int qstride = W == 1 ? ScanCfg<1>::QSTRIDE : W == 2 ? ScanCfg<2>::QSTRIDE : ScanCfg<4>::QSTRIDE;
+  const int hb = W == 1 ? ScanCfg<1>::HB : W == 2 ? ScanCfg<2>::HB : ScanCfg<4>::HB;
   const uint32_t step = W == 1 ? ScanCfg<1>::STEP : W == 2 ? ScanCfg<2>::STEP : ScanCfg<4>::STEP;
   ScanParams p;
   p.codes = (const uint4*)ix->d_codes; p.n = ix->n; p.first_id = ix->first_id;
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k;
-  p.BUF = pow2_at_least(k + kScanThreads);
+  p.BUF = pow2_at_least(k + kScanSub);
   p.compact_at = k + (p.BUF - k) / 2;
-  // query tile: as many queries as fit the shared-memory budget (default: two CTAs per SM)
-  const size_t per_q = scan_smem_bytes(1, p.BUF, qstride) - 16;
-  const size_t budget = ix->scan_smem_kb > 0 ? (size_t)ix->scan_smem_kb * 1024 : (ix->smem_optin > 220 * 1024 ? 110 * 1024 : ix->smem_optin / 2);
-  uint32_t qt = (uint32_t)std::max<size_t>(1, (std::min(budget, ix->smem_optin) - 16) / per_q);
+  // shared memory plan: [ring: stages x 16 KB][per-query state x QT].  Default: two CTAs per SM, the query
+  // tile gets up to 64 KB, the ring whatever is left (2..8 stages).
+  const size_t fixed = scan_smem_bytes(0, p.BUF, qstride, 0);
+  const size_t per_q = scan_smem_bytes(1, p.BUF, qstride, 0) - fixed;
+  const size_t cta_budget = (ix->smem_optin + 1024) / std::max<int64_t>(1, ix->scan_ctas_per_sm) - 2048;
+  const size_t state_budget = ix->scan_smem_kb > 0 ? (size_t)ix->scan_smem_kb * 1024 : (size_t)64 * 1024;
+  uint32_t qt = (uint32_t)std::max<size_t>(1, (std::max(state_budget, fixed + per_q) - fixed) / per_q);
   if (ix->scan_qt > 0) qt = (uint32_t)ix->scan_qt;
   qt = std::min(qt, nq);
-  while (scan_smem_bytes(qt, p.BUF, qstride) > ix->smem_optin && qt > 1) --qt;
-  if (scan_smem_bytes(qt, p.BUF, qstride) > ix->smem_optin) return fail(VC_ERR_ARG, "k = %u needs more shared memory than the device has", k);
-  p.QT = qt;
+  auto total_smem = [&](uint32_t q, uint32_t stg) { return scan_smem_bytes(q, p.BUF, qstride, stg); };
+  uint32_t stages = 2;
+  if (ix->scan_stages > 0) stages = (uint32_t)std::min<int64_t>(ix->scan_stages, kScanMaxStages);
+  else while (stages < kScanMaxStages && total_smem(qt, stages + 1) <= cta_budget) ++stages;
+  while (total_smem(qt, stages) > ix->smem_optin && stages > 2) --stages;
+  while (total_smem(qt, stages) > ix->smem_optin && qt > 1) --qt;
+  if (total_smem(qt, stages) > ix->smem_optin) return fail(VC_ERR_ARG, "k = %u needs more shared memory than the device has", k);
+  p.QT = qt; p.stages = stages;
   p.n_qtiles = (nq + qt - 1) / qt;
-  const size_t smem = scan_smem_bytes(qt, p.BUF, qstride);
-  bool pf = ix->scan_prefilter < 0 ? (W <= 2) : ix->scan_prefilter != 0;
+  const size_t smem = total_smem(qt, stages);
+  // the half-POPC lower-bound test pays once the kernel is POPC-bound (a handful of queries per code)
+  bool pf = ix->scan_prefilter < 0 ? (W <= 2 && nq >= 4) : ix->scan_prefilter != 0;
   int occ = 1, rc;
   if (W == 1) rc = pf ? scan_occupancy<1, true>(smem, &occ) : scan_occupancy<1, false>(smem, &occ);
   else if (W == 2) rc = pf ? scan_occupancy<2, true>(smem, &occ) : scan_occupancy<2, false>(smem, &occ);
@@ -557,14 +577,30 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   const uint64_t capacity = (uint64_t)occ * ix->num_sms;
   const uint64_t waves = ix->scan_waves > 0 ? (uint64_t)ix->scan_waves : ((uint64_t)p.n_qtiles * 8 <= capacity ? 1 : 8);
   const uint64_t n_steps = std::max<uint64_t>(1, (ix->n + step - 1) / step);
-  uint64_t slices = std::max<uint64_t>(1, (capacity * waves + p.n_qtiles - 1) / p.n_qtiles);
+  // one wave: never spill a few CTAs into a second, almost empty wave (round down); several waves: round up
+  uint64_t slices = waves == 1 ? std::max<uint64_t>(1, capacity / p.n_qtiles)
+                               : std::max<uint64_t>(1, (capacity * waves + p.n_qtiles - 1) / p.n_qtiles);
   slices = std::min(slices, n_steps);
   const uint64_t steps_per_slice = (n_steps + slices - 1) / slices;
   p.slice_codes = steps_per_slice * step;
   p.n_slices = (uint32_t)((n_steps + steps_per_slice - 1) / steps_per_slice);
+  p.interleave = ix->scan_interleave ? 1u : 0u;
   ix->last_scan_grid = (int64_t)p.n_qtiles * p.n_slices; ix->last_scan_qt = qt; ix->last_scan_slices = p.n_slices;
-  ix->last_scan_smem = (int64_t)smem; ix->last_scan_occ = occ;
+  ix->last_scan_smem = (int64_t)smem; ix->last_scan_occ = occ; ix->last_scan_stages = stages;
 
+  rc = ix->d_gstate.ensure((size_t)nq * (hb + 1) * 4);
+  if (rc) return rc;
+  p.gtau = (uint32_t*)ix->d_gstate.p;
+  p.ghist = p.gtau + nq;            // nq is padded below to keep the histogram rows 16-byte aligned
+  {
+    const uint32_t nq_pad = (nq + 3) & ~3u;
+    rc = ix->d_gstate.ensure(((size_t)nq_pad + (size_t)nq * hb) * 4);
+    if (rc) return rc;
+    p.gtau = (uint32_t*)ix->d_gstate.p;
+    p.ghist = p.gtau + nq_pad;
+    scan_init_kernel<<<grid_for((uint64_t)nq * hb, 256, ix->num_sms), 256, 0, st>>>(p.gtau, p.ghist, nq, (uint32_t)hb);
+    ix->launches++;
+  }
   const uint32_t fanin = (uint32_t)std::max<int64_t>(2, ix->merge_fanin);
   const size_t part_keys = (size_t)p.n_slices * nq * k;
   rc = ix->d_partial.ensure(part_keys * 8);
@@ -595,7 +631,9 @@ static int launch_mih(vc_index* ix, const MihParams& p, cudaStream_t st) {
   auto kern = mih_search_kernel<W, APPROX>;
   const size_t smem = (size_t)p.BUFM * 8 + (size_t)kMihWarps * kMihWbuf * 8;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  if (ix->profile) cudaEventRecord(ix->ev0, st);
   kern<<<p.nq, kMihThreads, smem, st>>>(p);
+  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; }
   ix->launches++;
   CU(cudaGetLastError());
   return VC_OK;
@@ -680,8 +718,16 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   if (!strcmp(name, "scan.prefilter")) ix->scan_prefilter = value;
   else if (!strcmp(name, "scan.qt")) ix->scan_qt = value;
   else if (!strcmp(name, "scan.waves")) ix->scan_waves = value;
+  else if (!strcmp(name, "scan.stages")) ix->scan_stages = value;
+  else if (!strcmp(name, "scan.interleave")) ix->scan_interleave = value;
+  else if (!strcmp(name, "scan.ctas_per_sm")) ix->scan_ctas_per_sm = value;
   else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
   else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
+  else if (!strcmp(name, "profile")) {
+    DeviceGuard g(ix->device);
+    if (value && !ix->ev0) { CU(cudaEventCreate(&ix->ev0)); CU(cudaEventCreate(&ix->ev1)); }
+    ix->profile = value; ix->ev_valid = false;
+  }
   else return fail(VC_ERR_ARG, "unknown parameter '%s'", name);
   return VC_OK;
 }
@@ -699,7 +745,19 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "scan.last_slices")) *value = ix->last_scan_slices;
   else if (!strcmp(name, "scan.last_smem")) *value = ix->last_scan_smem;
   else if (!strcmp(name, "scan.last_occ")) *value = ix->last_scan_occ;
+  else if (!strcmp(name, "scan.last_stages")) *value = ix->last_scan_stages;
+  else if (!strcmp(name, "scan.stages")) *value = ix->scan_stages;
   else if (!strcmp(name, "num_sms")) *value = ix->num_sms;
+  else if (!strcmp(name, "profile")) *value = ix->profile;
+  else if (!strcmp(name, "last_kernel_ns")) {
+    // device time of the dominant kernel (scan_topk / mih_search) of the last search; waits for it
+    if (!ix->profile || !ix->ev_valid) return fail(VC_ERR_STATE, "profiling is off or no search has run");
+    DeviceGuard g(ix->device);
+    float ms = 0.f;
+    CU(cudaEventSynchronize(ix->ev1));
+    CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+    *value = (int64_t)((double)ms * 1e6);
+  }
   else return fail(VC_ERR_ARG, "unknown parameter '%s'", name);
   return VC_OK;
 }

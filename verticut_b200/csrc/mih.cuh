@@ -109,7 +109,7 @@ __device__ __forceinline__ void mih_flush(uint64_t* mbuf, volatile uint64_t* tau
 
 template <int W, bool APPROX>
 __global__ void __launch_bounds__(kMihThreads) mih_search_kernel(const MihParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* mbuf = (uint64_t*)smem_raw;
   uint64_t* wbuf_all = mbuf + p.BUFM;
   __shared__ uint64_t s_tau_key;

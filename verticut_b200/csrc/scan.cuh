@@ -5,144 +5,249 @@
 // canonical tie rule (k smallest packed words dist<<32|id, ascending).
 //
 // Decomposition: the database shard is cut into `n_slices` contiguous slices, the query batch into
-// `n_qtiles` tiles of QT queries.  One CTA owns one (slice, query-tile): it keeps the QT queries,
-// their thresholds and their candidate buffers in shared memory, streams the slice through
-// registers (4 x 128-bit loads per thread per step) and tests every code against every query of
-// the tile.  Codes whose distance does not beat the query's current k-th best (the common case)
-// cost XOR + POPC + MIN only; the rare survivors are appended to the query's shared-memory buffer,
-// which a warp compacts with a bitonic sort when it fills.  Each CTA finally writes its k best
-// per query; merge_topk_kernel folds the n_slices partial lists (and, multi-GPU, the all-gathered
-// per-shard lists) into the final answer.  No global atomics, no host round trips.
+// `n_qtiles` tiles of QT queries.  One CTA owns one (slice, query-tile):
+//   * a producer warp streams the slice into a shared-memory ring with 1-D bulk async copies
+//     (cp.async.bulk, completion on an mbarrier) - 16 KB stages, so the bytes in flight do not depend on
+//     registers or occupancy;
+//   * 8 consumer warps lift their 64 bytes of each stage into registers (conflict-free LDS.128) and test
+//     every code against every query of the tile: XOR + POPC + 3-input MIN per (code, query), one compare
+//     and one branch per 8 codes.  With PREFILTER the test uses popc(x_lo | x_hi) <= popc(x_lo) + popc(x_hi),
+//     a lower bound of the distance that needs half the POPCs; survivors are re-checked exactly.
+//   * the per-query distance threshold tau is shared by ALL CTAs of the launch: every appended code is
+//     counted once in a global per-query distance histogram, tau = the smallest d with at least k codes
+//     counted at distance <= d (a valid upper bound of the final k-th distance), lowered with atomicMin
+//     and re-read by every CTA at each step - so the whole grid learns the threshold together and only
+//     ~k*ln(N/k) codes per query ever leave the fast path;
+//   * the rare survivors go to the query's candidate buffer; a warp compacts it with a bitonic sort when
+//     it fills.  Overflow (ties, first step) rolls the step back and replays it one sub-column at a time.
+// Each CTA finally writes its k best per query; merge_topk_kernel folds the n_slices partial lists (and,
+// multi-GPU, the all-gathered per-shard lists).  No global atomics, no host round trips.
 #pragma once
 #include "common.cuh"
 
 namespace vc {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 256;                          // consumer threads
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kScanU4PerThread = 4;                       // 64 bytes per thread per step
+constexpr int kScanCtaThreads = kScanThreads + 32;         // + one producer warp
+constexpr int kScanU4PerThread = 4;                        // 64 bytes per consumer thread per step
+constexpr int kScanStageBytes = kScanThreads * kScanU4PerThread * 16;   // 16 KB
+constexpr int kScanSub = 128;                              // threads appending at once on the careful path
+constexpr int kScanMaxStages = 8;
 
 struct ScanParams {
-  const uint4* codes;        // shard codes, [n][W] u64, 16-byte aligned
+  const uint4* codes;        // shard codes, [n][W] u64, 16-byte aligned, padded
   uint64_t n;                // codes in the shard
   uint32_t first_id;         // global id of code 0
   const uint32_t* queries;   // [nq][2W] u32
   uint32_t nq, k;
   uint32_t QT;               // queries per CTA
-  uint32_t BUF;              // candidate-buffer entries per query: power of two >= k + kScanThreads
+  uint32_t BUF;              // candidate-buffer entries per query: power of two >= k + kScanSub
   uint32_t compact_at;       // compact a buffer once it holds this many entries
+  uint32_t stages;           // ring depth
   uint32_t n_qtiles, n_slices;
   uint64_t slice_codes;      // codes per slice (multiple of the step size)
+  uint32_t interleave;       // 1: slice j = steps j, j + n_slices, ... (all CTAs stream one narrow address window)
   uint64_t* partial;         // [n_slices][nq][k]
+  uint32_t* gtau;            // [nq]     launch-wide distance thresholds (initialised to kInfDist)
+  uint32_t* ghist;           // [nq][HB] launch-wide distance histograms of appended codes (initialised to 0)
 };
 
 template <int W> struct ScanCfg {
   static constexpr int C = 2 * kScanU4PerThread / W;        // codes per thread per step (8 / 4 / 2)
   static constexpr int STEP = kScanThreads * C;             // codes per CTA step (2048 / 1024 / 512)
   static constexpr int QSTRIDE = (2 * W + 1 + 3) / 4 * 4;   // u32 per query record: 2W query words, tau, pad
+  static constexpr int HB = 64 * W + 32;                    // histogram bins per query (distances 0..64W)
 };
 
-struct ScanSmem {
-  uint64_t* buf;      // [QT][BUF]
-  uint64_t* tau_key;  // [QT]
-  uint32_t* qrec;     // [QT][QSTRIDE]  query words then the distance threshold
-  uint32_t* cnt;      // [QT]
-  uint32_t* cnt0;     // [QT] count at step start (roll-back point)
-  uint32_t* ovf;      // [QT] 1 = needs the careful path this step
-  uint32_t* any_ovf;  // [1]
-};
-
-__host__ __device__ inline size_t scan_smem_bytes(uint32_t QT, uint32_t BUF, int qstride) {
-  return (size_t)QT * BUF * 8 + (size_t)QT * 8 + (size_t)QT * qstride * 4 + (size_t)QT * 12 + 16;
+// ---- PTX: mbarrier + 1-D bulk async copy (TMA engine, no tensor map needed) --------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// barrier over the consumer threads only (id 1), with an OR-reduction of a predicate
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kScanThreads) : "memory"); }
+__device__ __forceinline__ uint32_t consumer_sync_or(uint32_t pred) {
+  uint32_t r;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbar.red.or.pred q, 1, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(r) : "r"(pred), "n"(kScanThreads) : "memory");
+  return r;
 }
 
-__device__ __forceinline__ ScanSmem scan_carve(unsigned char* base, uint32_t QT, uint32_t BUF, int qstride) {
-  ScanSmem s;                                   // every section stays 16-byte aligned for uint4 reads of qrec
-  s.buf = (uint64_t*)base;
+// ---- shared-memory layout -----------------------------------------------------------------------------
+struct ScanSmem {
+  unsigned char* ring;  // [stages][kScanStageBytes]
+  uint64_t* buf;        // [QT][BUF]
+  uint32_t* qrec;       // [QT][QSTRIDE]  query words, then the distance threshold tau
+  uint64_t* tau_key;    // [QT] k-th best packed word at the last compaction
+  uint32_t* cnt;        // [QT]
+  uint32_t* cnt0;       // [QT] count at step start (roll-back point)
+  uint32_t* flag;       // [QT] 1 = overflowed this step / needs the careful path
+  uint64_t* full;       // [stages]
+  uint64_t* empty;      // [stages]
+};
+
+__host__ __device__ inline size_t scan_smem_bytes(uint32_t QT, uint32_t BUF, int qstride, uint32_t stages) {
+  return (size_t)stages * kScanStageBytes + (size_t)QT * BUF * 8 + (size_t)QT * qstride * 4 + (size_t)QT * 8 +
+         (size_t)QT * 12 + 16 + (size_t)2 * kScanMaxStages * 8;
+}
+
+__device__ __forceinline__ ScanSmem scan_carve(unsigned char* base, uint32_t QT, uint32_t BUF, int qstride, uint32_t stages) {
+  ScanSmem s;                                   // every section stays 16-byte aligned
+  s.ring = base;
+  s.buf = (uint64_t*)(base + (size_t)stages * kScanStageBytes);
   s.qrec = (uint32_t*)(s.buf + (size_t)QT * BUF);
   s.tau_key = (uint64_t*)(s.qrec + (size_t)QT * qstride);
   s.cnt = (uint32_t*)(s.tau_key + QT);
   s.cnt0 = s.cnt + QT;
-  s.ovf = s.cnt0 + QT;
-  s.any_ovf = s.ovf + QT;
+  s.flag = s.cnt0 + QT;
+  s.full = (uint64_t*)(((uintptr_t)(s.flag + QT) + 15) & ~(uintptr_t)15);
+  s.empty = s.full + kScanMaxStages;
   return s;
 }
 
-// Rare path of the fast loop: exact distance, exact (dist,id) test, append or flag overflow.
-template <int W>
-__device__ __noinline__ void scan_append(const ScanSmem s, uint32_t BUF, int qstride, uint32_t q, CodeRegs<W> c, uint32_t id) {
-  const uint32_t* qr = s.qrec + q * qstride;
-  uint32_t d = 0;
+// Lowers the launch-wide threshold of one query from its global histogram: tau = smallest d with at
+// least k codes counted at distance <= d.  Concurrent increments may be missed (counts only grow), which
+// can only make the result larger, i.e. still a valid bound.
+__device__ __forceinline__ void scan_update_tau(const uint32_t* gh, int hb, uint32_t k, uint32_t lim, uint32_t* gtau_q, uint32_t* stau_q) {
+  uint32_t c = 0;
+  for (uint32_t j = 0; j < lim; j += 4) {            // 16-byte L2 reads, independent of each other
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(gh + j));
+    const uint32_t e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < 2 * W; ++i) d += __popc(c.w[i] ^ qr[i]);
-  uint64_t key = pack_key(d, id);
-  if (key < s.tau_key[q]) {
-    uint32_t slot = atomicAdd(&s.cnt[q], 1u);
-    if (slot < BUF) s.buf[(size_t)q * BUF + slot] = key;
-    else { s.ovf[q] = 1; *s.any_ovf = 1; }
+    for (int t = 0; t < 4; ++t) {
+      c += e[t];
+      if (c >= k && j + t < lim) { atomicMin(gtau_q, j + t); atomicMin(stau_q, j + t); return; }
+    }
   }
 }
 
+// Rare path of the fast loop: a code whose exact distance d passed the threshold.  Appends it to the
+// query's buffer (flagging overflow), counts it in the launch-wide histogram and tightens tau.
+__device__ __noinline__ void scan_append(unsigned char* smem, uint32_t QT, uint32_t BUF, uint32_t stages, int qstride, int hb,
+                                         uint32_t tau_off, uint32_t k, uint32_t q, uint32_t d, uint32_t id,
+                                         uint32_t* gtau_q, uint32_t* gh) {
+  const ScanSmem s = scan_carve(smem, QT, BUF, qstride, stages);
+  const uint64_t key = pack_key(d, id);
+  if (key >= s.tau_key[q]) return;
+  const uint32_t slot = atomicAdd(&s.cnt[q], 1u);
+  if (slot < BUF) s.buf[(size_t)q * BUF + slot] = key;
+  else s.flag[q] = 1;
+  atomicAdd(&gh[d], 1u);
+  uint32_t* stau_q = s.qrec + q * qstride + tau_off;
+  const uint32_t tau = *(volatile uint32_t*)stau_q;
+  if (d < tau) scan_update_tau(gh, hb, k, min(tau, (uint32_t)hb), gtau_q, stau_q);   // only a code strictly inside can lower it
+}
+
 template <int W, bool PREFILTER>
-__global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanParams p) {
   using Cfg = ScanCfg<W>;
-  constexpr int C = Cfg::C, QS = Cfg::QSTRIDE;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ScanSmem s = scan_carve(smem_raw, p.QT, p.BUF, QS);
+  constexpr int C = Cfg::C, QS = Cfg::QSTRIDE, HB = Cfg::HB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ScanSmem s = scan_carve(smem_raw, p.QT, p.BUF, QS, p.stages);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t qtile = blockIdx.x % p.n_qtiles, slice = blockIdx.x / p.n_qtiles;
   const uint32_t q0 = qtile * p.QT;
   const uint32_t nq_here = min(p.QT, p.nq - q0);
-  const uint32_t BUF = p.BUF;
+  const uint32_t BUF = p.BUF, S = p.stages;
+  // contiguous: steps [slice*spp, ...) of the shard; interleaved: steps slice, slice + n_slices, ...
+  const uint64_t total_steps = (p.n + Cfg::STEP - 1) / Cfg::STEP;
+  const uint64_t spp = p.slice_codes / Cfg::STEP;
+  const uint64_t step0 = p.interleave ? slice : (uint64_t)slice * spp;
+  const uint64_t stride = p.interleave ? p.n_slices : 1;
+  const uint32_t n_steps = p.interleave ? (uint32_t)(total_steps > slice ? (total_steps - slice + p.n_slices - 1) / p.n_slices : 0)
+                                        : (uint32_t)(total_steps > step0 ? min(spp, total_steps - step0) : 0);
+  const uint64_t end = p.n;
 
-  // ---- stage the query tile --------------------------------------------------------------
-  for (uint32_t i = tid; i < nq_here * QS; i += kScanThreads) {
-    uint32_t q = i / QS, j = i % QS;
+  // ---- set-up: query tile, counters, barriers ------------------------------------------------------
+  for (uint32_t i = tid; i < nq_here * QS; i += kScanCtaThreads) {
+    const uint32_t q = i / QS, j = i % QS;
     s.qrec[i] = j < 2 * W ? p.queries[(size_t)(q0 + q) * 2 * W + j] : (j == 2 * W ? kInfDist : 0u);
   }
-  for (uint32_t q = tid; q < nq_here; q += kScanThreads) {
-    s.tau_key[q] = kEmptyKey; s.cnt[q] = 0; s.cnt0[q] = 0; s.ovf[q] = 1;   // first step: careful path
+  for (uint32_t q = tid; q < nq_here; q += kScanCtaThreads) {
+    s.tau_key[q] = kEmptyKey; s.cnt[q] = 0; s.cnt0[q] = 0; s.flag[q] = 1;   // first step: careful path
   }
-  if (tid == 0) *s.any_ovf = 1;
+  if (tid == 0) {
+    for (uint32_t i = 0; i < S; ++i) { mbar_init(&s.full[i], 1); mbar_init(&s.empty[i], kScanWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
-  const uint64_t beg = (uint64_t)slice * p.slice_codes;
-  const uint64_t end = min(p.n, beg + p.slice_codes);
+  if (warp == kScanWarps) {
+    // ===== producer warp: one lane feeds the ring =====================================================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (uint32_t i = 0; i < n_steps; ++i, st = (st + 1 == S ? 0 : st + 1), ph ^= (st == 0)) {
+        mbar_wait(&s.empty[st], ph ^ 1);
+        const uint64_t base = (step0 + (uint64_t)i * stride) * Cfg::STEP;
+        const uint64_t codes_here = min((uint64_t)Cfg::STEP, end - base);
+        const uint32_t bytes = (uint32_t)((codes_here * W * 8 + 15) & ~15ull);
+        mbar_arrive_expect_tx(&s.full[st], bytes);
+        bulk_g2s(s.ring + (size_t)st * kScanStageBytes, p.codes + base * W / 2, bytes, &s.full[st]);
+      }
+    }
+    return;
+  }
 
-  for (uint64_t base = beg; base < end; base += Cfg::STEP) {
-    // ---- load this step's codes: unit u of thread t = uint4 (base*W/2 + u*T + t) ------------
+  // ===== consumer warps ==================================================================================
+  uint32_t careful = 1;                 // CTA-uniform: this step must take the careful path
+  uint32_t first_settle = 1;            // the first settle seeds the launch-wide histogram with the kept entries
+  uint32_t st = 0, ph = 0;
+  for (uint32_t i = 0; i < n_steps; ++i, st = (st + 1 == S ? 0 : st + 1), ph ^= (st == 0)) {
+    const uint64_t base = (step0 + (uint64_t)i * stride) * Cfg::STEP;
     CodeRegs<W> code[C];
-    uint32_t local[C];            // index of the code inside the step
+    // pick up the launch-wide thresholds the other CTAs have reached (one L2 read per query, off the critical path)
+    uint32_t gt = kInfDist;
+    if (tid < nq_here) gt = __ldcg(p.gtau + q0 + tid);
+    mbar_wait(&s.full[st], ph);
     {
-      const uint64_t u4_base = base * W / 2;               // 16-byte units (base is a STEP multiple)
-      const uint64_t u4_end = (p.n * W + 1) / 2;           // units that exist (last may be half-valid when W=1)
+      const uint4* stage = reinterpret_cast<const uint4*>(s.ring + (size_t)st * kScanStageBytes);
 #pragma unroll
       for (int u = 0; u < kScanU4PerThread; ++u) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if constexpr (W == 1) {          // one unit = two codes
-          const uint64_t idx = u4_base + (uint64_t)u * kScanThreads + tid;
-          if (idx < u4_end) v = ld_stream_u4(p.codes + idx);
+        if constexpr (W == 1) {          // unit = two codes: local index 2*(u*T + t) + h
+          const uint4 v = stage[u * kScanThreads + tid];
           code[2 * u].w[0] = v.x; code[2 * u].w[1] = v.y;
           code[2 * u + 1].w[0] = v.z; code[2 * u + 1].w[1] = v.w;
-          local[2 * u] = 2 * (u * kScanThreads + tid);
-          local[2 * u + 1] = 2 * (u * kScanThreads + tid) + 1;
-        } else if constexpr (W == 2) {   // one unit = one code
-          const uint64_t idx = u4_base + (uint64_t)u * kScanThreads + tid;
-          if (idx < u4_end) v = ld_stream_u4(p.codes + idx);
+        } else if constexpr (W == 2) {   // unit = one code: local index u*T + t
+          const uint4 v = stage[u * kScanThreads + tid];
           code[u].w[0] = v.x; code[u].w[1] = v.y; code[u].w[2] = v.z; code[u].w[3] = v.w;
-          local[u] = u * kScanThreads + tid;
-        } else {                         // W == 4: two consecutive units = one code
+        } else {                         // W == 4: code c = units 2*(c*T + t), +1: local index c*T + t
           const int cc = u / 2, h = u % 2;
-          const uint64_t idx = u4_base + 2 * ((uint64_t)cc * kScanThreads + tid) + h;
-          if (idx < u4_end) v = ld_stream_u4(p.codes + idx);
+          const uint4 v = stage[2 * (cc * kScanThreads + tid) + h];
           code[cc].w[4 * h + 0] = v.x; code[cc].w[4 * h + 1] = v.y; code[cc].w[4 * h + 2] = v.z; code[cc].w[4 * h + 3] = v.w;
-          local[cc] = cc * kScanThreads + tid;
         }
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.empty[st]);          // stage may be refilled while we compute
+    if (tid < nq_here && gt < s.qrec[tid * QS + 2 * W]) atomicMin(&s.qrec[tid * QS + 2 * W], gt);
+    auto local_of = [&](int c) -> uint32_t {
+      if constexpr (W == 1) return 2 * ((c / 2) * kScanThreads + tid) + (c & 1);
+      else return c * kScanThreads + tid;
+    };
 
-    if (*s.any_ovf == 0) {
-      // ---- fast path: every query of the tile against the C codes in registers --------------
+    uint32_t appended = 0;
+    if (!careful) {
+      // ---- fast path: every query of the tile against the C codes in registers ---------------------
 #pragma unroll 1
       for (uint32_t q = 0; q < nq_here; ++q) {
         uint32_t qw[2 * W];
@@ -153,9 +258,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
           qw[0] = r.x; qw[1] = r.y; tau = r.z;
         } else {
 #pragma unroll
-          for (int i = 0; i < W / 2; ++i) {
-            const uint4 r = qv[i];
-            qw[4 * i] = r.x; qw[4 * i + 1] = r.y; qw[4 * i + 2] = r.z; qw[4 * i + 3] = r.w;
+          for (int j = 0; j < W / 2; ++j) {
+            const uint4 r = qv[j];
+            qw[4 * j] = r.x; qw[4 * j + 1] = r.y; qw[4 * j + 2] = r.z; qw[4 * j + 3] = r.w;
           }
           tau = s.qrec[q * QS + 2 * W];
         }
@@ -168,66 +273,118 @@ __global__ void __launch_bounds__(kScanThreads) scan_topk_kernel(const ScanParam
         }
         if (mn <= tau) {
 #pragma unroll
-          for (int c = 0; c < C; ++c)
-            if (m[c] <= tau && base + local[c] < end)
-              scan_append<W>(s, BUF, QS, q, code[c], p.first_id + (uint32_t)(base + local[c]));
+          for (int c = 0; c < C; ++c) {
+            if (m[c] <= tau) {
+              const uint32_t d = PREFILTER ? hamming_exact<W>(code[c].w, qw) : m[c];
+              const uint64_t idx = base + local_of(c);
+              if (d <= tau && idx < end) {
+                scan_append(smem_raw, p.QT, BUF, S, QS, HB, 2 * W, p.k, q, d, p.first_id + (uint32_t)idx,
+                            p.gtau + q0 + q, p.ghist + (size_t)(q0 + q) * HB);
+                appended = 1;
+              }
+            }
+          }
         }
       }
     }
-    __syncthreads();
+    // one barrier per step; it also tells every thread whether anything was appended
+    const uint32_t any = consumer_sync_or(appended | careful);
+    if (!any) continue;
 
-    // ---- step epilogue: roll back overflowed queries, compact full buffers ---------------------
-    if (*s.any_ovf) {
-      // careful path (first step of the CTA, or a buffer overflowed): one code column at a time,
-      // with room for a full column guaranteed before each.
+    // ---- step epilogue ---------------------------------------------------------------------------------
+    uint32_t need_careful = careful;
+    if (!careful) {
+      uint32_t f = 0;
+      for (uint32_t q = tid; q < nq_here; q += kScanThreads) f |= s.flag[q];
+      need_careful = consumer_sync_or(f);
+    }
+    if (need_careful) {
+      // overflowed queries (all of them on the first step): roll the step back, then replay it one
+      // sub-column (kScanSub threads x one code) at a time with room guaranteed before each
       for (uint32_t q = tid; q < nq_here; q += kScanThreads)
-        if (s.ovf[q]) s.cnt[q] = s.cnt0[q];
-      __syncthreads();
+        if (s.flag[q]) s.cnt[q] = s.cnt0[q];
+      consumer_sync();
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        for (uint32_t q = warp; q < nq_here; q += kScanWarps) {
-          if (s.ovf[q] && s.cnt[q] + kScanThreads > BUF) {
-            uint64_t tau = topk_compact(s.buf + (size_t)q * BUF, &s.cnt[q], BUF, p.k, lane, 32, WarpSync());
-            if (lane == 0) { s.tau_key[q] = tau; s.qrec[q * QS + 2 * W] = tau == kEmptyKey ? kInfDist : (uint32_t)(tau >> 32); }
+        const uint64_t idx = base + local_of(c);
+        const bool valid = idx < end;
+        const uint32_t id = p.first_id + (uint32_t)idx;
+        for (uint32_t half = 0; half < kScanThreads / kScanSub; ++half) {
+          for (uint32_t q = warp; q < nq_here; q += kScanWarps) {
+            if (s.flag[q] && s.cnt[q] + kScanSub > BUF) {
+              const uint64_t tk = topk_compact(s.buf + (size_t)q * BUF, &s.cnt[q], BUF, p.k, lane, 32, WarpSync());
+              if (lane == 0) {
+                s.tau_key[q] = tk;
+                if (tk != kEmptyKey) atomicMin(&s.qrec[q * QS + 2 * W], (uint32_t)(tk >> 32));
+              }
+            }
           }
-        }
-        __syncthreads();
-        const bool valid = base + local[c] < end;
-        const uint32_t id = p.first_id + (uint32_t)(base + local[c]);
-        for (uint32_t q = 0; q < nq_here; ++q) {
-          if (!s.ovf[q]) continue;
-          const uint32_t* qr = s.qrec + q * QS;
-          uint32_t d = 0;
+          consumer_sync();
+          if (tid / kScanSub == half) {
+            for (uint32_t q = 0; q < nq_here; ++q) {
+              if (!s.flag[q]) continue;
+              const uint32_t* qr = s.qrec + q * QS;
+              uint32_t d = 0;
 #pragma unroll
-          for (int i = 0; i < 2 * W; ++i) d += __popc(code[c].w[i] ^ qr[i]);
-          const uint64_t key = pack_key(d, id);
-          if (valid && key < s.tau_key[q]) {
-            uint32_t slot = atomicAdd(&s.cnt[q], 1u);
-            s.buf[(size_t)q * BUF + slot] = key;      // slot < BUF by construction
+              for (int j = 0; j < 2 * W; ++j) d += __popc(code[c].w[j] ^ qr[j]);
+              const uint64_t key = pack_key(d, id);
+              if (valid && d <= qr[2 * W] && key < s.tau_key[q]) {
+                const uint32_t slot = atomicAdd(&s.cnt[q], 1u);
+                s.buf[(size_t)q * BUF + slot] = key;      // slot < BUF by construction
+              }
+            }
           }
+          consumer_sync();
         }
-        __syncthreads();
       }
-      for (uint32_t q = tid; q < nq_here; q += kScanThreads) s.ovf[q] = 0;
-      if (tid == 0) *s.any_ovf = 0;
-      __syncthreads();
+      // settle the replayed queries: compact; on the very first step also count the kept entries in the
+      // launch-wide histogram (every code is counted there exactly once: here, or when the fast path appends it)
+      for (uint32_t q = warp; q < nq_here; q += kScanWarps) {
+        if (!s.flag[q]) continue;
+        const uint64_t tk = topk_compact(s.buf + (size_t)q * BUF, &s.cnt[q], BUF, p.k, lane, 32, WarpSync());
+        if (first_settle) {
+          uint32_t* gh = p.ghist + (size_t)(q0 + q) * HB;
+          const uint32_t kept = s.cnt[q];
+          for (uint32_t e = lane; e < kept; e += 32) atomicAdd(&gh[(uint32_t)(s.buf[(size_t)q * BUF + e] >> 32)], 1u);
+          __syncwarp();
+          if (lane == 0) scan_update_tau(gh, HB, p.k, HB, p.gtau + q0 + q, &s.qrec[q * QS + 2 * W]);
+        }
+        if (lane == 0) {
+          s.tau_key[q] = tk;
+          if (tk != kEmptyKey) atomicMin(&s.qrec[q * QS + 2 * W], (uint32_t)(tk >> 32));
+          s.flag[q] = 0;
+        }
+      }
+      first_settle = 0;
     }
     for (uint32_t q = warp; q < nq_here; q += kScanWarps) {
       if (s.cnt[q] >= p.compact_at) {
-        uint64_t tau = topk_compact(s.buf + (size_t)q * BUF, &s.cnt[q], BUF, p.k, lane, 32, WarpSync());
-        if (lane == 0) { s.tau_key[q] = tau; s.qrec[q * QS + 2 * W] = tau == kEmptyKey ? kInfDist : (uint32_t)(tau >> 32); }
+        const uint64_t tk = topk_compact(s.buf + (size_t)q * BUF, &s.cnt[q], BUF, p.k, lane, 32, WarpSync());
+        if (lane == 0) {
+          s.tau_key[q] = tk;
+          if (tk != kEmptyKey) atomicMin(&s.qrec[q * QS + 2 * W], (uint32_t)(tk >> 32));
+        }
       }
       if (lane == 0) s.cnt0[q] = s.cnt[q];
     }
-    __syncthreads();
+    careful = 0;
+    consumer_sync();
   }
 
-  // ---- final compaction and partial-list write -------------------------------------------------
+  // ---- final compaction and partial-list write -------------------------------------------------------
   for (uint32_t q = warp; q < nq_here; q += kScanWarps) {
     topk_compact(s.buf + (size_t)q * BUF, &s.cnt[q], BUF, p.k, lane, 32, WarpSync());
     const uint32_t kept = s.cnt[q];
     uint64_t* out = p.partial + ((size_t)slice * p.nq + q0 + q) * p.k;
     for (uint32_t i = lane; i < p.k; i += 32) out[i] = i < kept ? s.buf[(size_t)q * BUF + i] : kEmptyKey;
+  }
+}
+
+// launch-wide thresholds / histograms of one search call
+__global__ void scan_init_kernel(uint32_t* gtau, uint32_t* ghist, uint32_t nq, uint32_t hb) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (uint64_t)nq * hb; i += (uint64_t)gridDim.x * blockDim.x) {
+    ghist[i] = 0;
+    if (i < nq) gtau[i] = kInfDist;
   }
 }
 
@@ -241,7 +398,7 @@ constexpr int kMergeThreads = 256;
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_t* __restrict__ lists, uint32_t n_lists, uint32_t fanin,
                                                                    uint32_t nq, uint32_t k, uint32_t BUF,
                                                                    uint64_t* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* buf = (uint64_t*)smem_raw;            // [BUF]
   __shared__ uint32_t cnt;
   __shared__ uint64_t tau_s;

@@ -1,0 +1,88 @@
+"""Id-sharded search over the GPUs of one box: one process per GPU, NCCL all-gather of the local top-k.
+
+Replaces the reference's distribution layer for this path - `mpirun -n m` with one rank per TABLE
+(src/search_worker.cc:58,99-101,225), MPI_Gatherv of every candidate to rank 0 and MPI_Bcast of the stop
+flag once per radius step (src/mpi_coordinator.cc:26-69, src/search_worker.cc:177,207) - by:
+
+  * rank g owns the contiguous id range [g*N/G, (g+1)*N/G) and ALL m tables over it (shard_range);
+  * queries are replicated; every rank answers them on its shard (exact local top-k; the MIH stop rule
+    is applied per shard, so no collective inside the radius loop);
+  * ONE all-gather of [nq][k] packed words (dist<<32|id) per batch over NVLink, then every rank folds
+    the G lists with merge_topk_kernel (shards are id-disjoint, so no de-duplication is needed).
+
+torch.distributed is plumbing here (process group, the all-gather, device buffers); searching and
+merging are the library's CUDA kernels, called through the C ABI with raw device pointers.
+"""
+import numpy as np
+
+from . import capi
+
+
+def shard_range(n_total, world_size, rank):
+    """[begin, end) of the ids owned by `rank`: contiguous, sizes differ by at most one code."""
+    base, rem = divmod(int(n_total), int(world_size))
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def gather_layout(world_size, nq, k):
+    """Shape of the all-gathered buffer the merge kernel consumes: [n_lists = G][nq][k] packed words."""
+    return (world_size, nq, k)
+
+
+class ShardedSearcher:
+    """One rank's view of the sharded database.
+
+    `index` is this rank's capi.Index (first_id = start of its id range).  `merge_fn(gathered, k)` is
+    injectable for CPU tests of the plumbing; by default the CUDA merge kernel is used.
+    """
+
+    def __init__(self, index, group=None, merge_fn=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.index = index
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.merge_fn = merge_fn
+        self._bufs = {}
+
+    def _buffers(self, nq, k, device):
+        key = (nq, k, str(device))
+        if key not in self._bufs:
+            t = self.torch
+            local = t.empty((nq, k), dtype=t.int64, device=device)
+            gathered = t.empty(gather_layout(self.world, nq, k), dtype=t.int64, device=device)
+            merged = t.empty((nq, k), dtype=t.int64, device=device)
+            self._bufs[key] = (local, gathered, merged)
+        return self._bufs[key]
+
+    def search(self, d_queries, k, mode="mih", approximate=False, max_radius=-1):
+        """d_queries: uint8 tensor [nq, code_bytes] on this rank's GPU.  Returns an int64 tensor [nq, k] of
+        packed words (bit pattern of uint64, ascending), identical on every rank."""
+        t = self.torch
+        nq = d_queries.shape[0]
+        local, gathered, merged = self._buffers(nq, k, d_queries.device)
+        stream = t.cuda.current_stream().cuda_stream
+        if mode == "mih":
+            self.index.search_mih_dev(d_queries.data_ptr(), nq, k, local.data_ptr(), approximate=approximate,
+                                      max_radius=max_radius, stream=stream)
+        elif mode == "linear":
+            self.index.search_linear_dev(d_queries.data_ptr(), nq, k, local.data_ptr(), stream=stream)
+        else:
+            raise ValueError("mode must be 'mih' or 'linear'")
+        if self.world == 1:
+            return local
+        self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
+        if self.merge_fn is not None:
+            return self.merge_fn(gathered, k)
+        capi.merge_topk_dev(self.index.device, gathered.data_ptr(), self.world, nq, k, merged.data_ptr(), stream=stream)
+        return merged
+
+
+def merge_gathered_host(gathered, k):
+    """Plumbing-test helper: the same fold on host arrays through the library's host-buffer merge."""
+    arr = np.ascontiguousarray(gathered, dtype=np.uint64)
+    return capi.merge_topk(0, arr, k)
