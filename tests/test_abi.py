@@ -1,0 +1,52 @@
+"""The C-ABI library loads and exports every symbol include/verticut_gpu.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "verticut_gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vc_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from verticut_b200 import capi
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), "libverticut_gpu.so does not export %s" % name
+    assert sorted(capi.EXPORTS) == names, "capi.EXPORTS and the header disagree"
+    assert lib.vc_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    # Without a CUDA device the product must fail loudly, not compute on the host.
+    from verticut_b200 import capi
+    try:
+        n = capi.device_count()
+    except capi.VerticutError:
+        n = 0
+    if n > 0:
+        pytest.skip("a device is present")
+    with pytest.raises(capi.VerticutError):
+        capi.Index(64, 4)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "verticut_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace("oracle/verticut_oracle.c", ""), f
+
+
+def test_synth_generator_matches_oracle(oracle):
+    from verticut_b200 import capi
+    for seed, idx, w in [(12345, 0, 0), (12345, 999_999_999, 0), (7, 123456, 3), (67890, 5, 1)]:
+        assert capi.synth_word(seed, idx, w) == oracle.lib().vo_synth_word(seed, idx, w)

@@ -1,0 +1,118 @@
+"""Pins the plain-C oracle (oracle/verticut_oracle.c) against the reference ITSELF (oracle/_ref: the reference's
+search_worker.cc / linear_search.cc / build_hash_tables.cc / integrity_check.cc compiled unmodified).
+CPU only.  Skipped only when neither /root/reference nor a prebuilt oracle/_ref exists."""
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as oracle_pkg
+from oracle import reference as F, restatement as R
+from helpers import check_p3
+
+if not F.available():
+    try:
+        oracle_pkg.build()
+    except Exception:
+        pass
+pytestmark = pytest.mark.skipif(not F.available(), reason="oracle/_ref not built (reference tree absent)")
+
+
+def _data(n, bits, nq, seed=12345):
+    return R.synth_codes(seed, 0, n, bits // 8), R.synth_codes(67890, 0, nq, bits // 8)
+
+
+@pytest.mark.parametrize("n,bits,m,k,nq,approx", [
+    (20000, 64, 4, 10, 10, False),
+    (30000, 64, 4, 100, 6, False),
+    (3000, 128, 8, 10, 3, False),
+    (6000, 64, 4, 10, 8, True),
+    (6000, 64, 4, 3, 5, True),
+    (40, 64, 4, 100, 3, False),       # fewer codes than k: the loop runs to r = s (search_worker.cc:170)
+])
+def test_restatement_reproduces_reference_mih_exactly(n, bits, m, k, nq, approx):
+    codes, queries = _data(n, bits, nq)
+    store = F.RefStore(codes, m)
+    rid, rd, rc, rrad, rsub = store.mih_search(queries, k, approximate=approx)
+    store.close()
+    ix = R.Index(codes, m)
+    oid, od, oc, ost = ix.search(queries, k, order=R.ORDER_REFERENCE, stop=R.STOP_REF4, approximate=approx)
+    np.testing.assert_array_equal(oc, rc)
+    np.testing.assert_array_equal(od, rd)        # same distances, same (descending) order
+    np.testing.assert_array_equal(oid, rid)      # same ids, including the libstdc++ heap tie order
+    for q in range(nq):
+        assert ost[q]["radius"] == rrad[q]
+        assert ost[q]["probes"] == rsub[q].sum()  # n_sub_reads_ (search_worker.cc:245), all ranks
+
+
+def test_restatement_reproduces_reference_linear_scan_exactly():
+    codes, queries = _data(30000, 64, 6)
+    store = F.RefStore(codes, 0)
+    store.put_main_table()
+    rid, rd, rc = store.linear_search(queries, 100)
+    store.close()
+    oid, od, oc = R.linear_search(codes, queries, 100, reference_order=True)
+    np.testing.assert_array_equal(oid, rid)
+    np.testing.assert_array_equal(od, rd)
+    np.testing.assert_array_equal(oc, rc)
+    mid, md, mc = F.RefMem(codes, 0).linear_search(queries, 100, n_procs=2)      # the CPU-baseline leg
+    np.testing.assert_array_equal(mid, rid)
+    np.testing.assert_array_equal(md, rd)
+
+
+@pytest.mark.parametrize("bits,m", [(64, 4), (128, 8), (64, 8)])
+def test_tables_match_reference_build(bits, m):
+    n = 5000
+    codes, _ = _data(n, bits, 1)
+    store = F.RefStore(codes, m)             # the reference's build-tables main(), rank by rank
+    mem = F.RefMem(codes, m)
+    ix = R.Index(codes, m)
+    sub = bits // m // 8
+    rng = np.random.default_rng(0)
+    for t in range(m):
+        for i in rng.integers(0, n, 8):
+            key = R.binary_to_int(codes[i, t * sub:(t + 1) * sub])
+            rc, ids, bcodes = store.bucket(t, key)
+            orc, oids = ix.bucket(t, key)
+            mrc, mids, _ = mem.bucket(t, key)
+            assert rc == orc == mrc == 0
+            np.testing.assert_array_equal(ids, oids)
+            np.testing.assert_array_equal(ids, mids)
+            np.testing.assert_array_equal(bcodes, codes[ids])
+            assert (np.diff(ids.astype(np.int64)) > 0).all()
+        key = int(rng.integers(0, 1 << (8 * sub)))
+        assert store.bucket(t, key)[0] == ix.bucket(t, key)[0]
+    store.close()
+
+
+def test_reference_integrity_check_passes_on_reference_tables():
+    # integrity_check.cc asserts (aborts) on failure, so it runs in a child process
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from oracle import reference as F, restatement as R\n"
+        "codes = R.synth_codes(12345, 0, 3000, 8)\n"
+        "s = F.RefStore(codes, 4)\n"
+        "assert s.integrity_check() == 0\n"
+        "s.close()\n" % oracle_pkg.HERE.rsplit('/', 1)[0]
+    )
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
+@pytest.mark.parametrize("n,bits,m,k", [(20000, 64, 4, 10), (30000, 64, 4, 100)])
+def test_contract_p3_p4_canonical_vs_reference(n, bits, m, k):
+    nq = 8
+    codes, queries = _data(n, bits, nq)
+    rid, rd, rc, rrad, _ = F.RefMem(codes, m).mih_search(queries, k)
+    ix = R.Index(codes, m)
+    cid, cd, cc, cst = ix.search(queries, k, order=R.ORDER_CANONICAL, stop=R.STOP_STRICT_M)
+    lid, ld, lc = R.linear_search(codes, queries, k)
+    np.testing.assert_array_equal(cid, lid)          # P2: canonical MIH == canonical scan
+    np.testing.assert_array_equal(cd, ld)
+    check_p3(cid, cd, cc, rid, rd, rc, lambda q, i: R.hamming(codes[i], queries[q]))
+    for q in range(nq):                              # P4 (m = 4)
+        dk = int(cd[q, : cc[q]].max())
+        assert cst[q]["radius"] in (rrad[q], rrad[q] + 1)
+        if cst[q]["radius"] != rrad[q]:
+            assert dk == 4 * (rrad[q] + 1)

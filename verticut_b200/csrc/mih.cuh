@@ -67,16 +67,6 @@ __device__ __forceinline__ uint32_t substring(const uint32_t* x, uint32_t t, uin
   return sbits == 32 ? v : (v & ((1u << sbits) - 1));
 }
 
-struct MihSmem {
-  uint64_t* mbuf;      // [BUFM] sorted best-so-far (first mcnt entries)
-  uint64_t* wbuf;      // [warps][kMihWbuf]
-  uint64_t tau_key;
-  uint32_t tau_dist;
-  uint32_t mcnt;
-  uint32_t lock;
-  uint32_t stop;
-};
-
 // Folds a warp's staging buffer into the per-query buffer.  Called by all 32 lanes.
 __device__ __forceinline__ void mih_flush(uint64_t* mbuf, volatile uint64_t* tau_key, volatile uint32_t* tau_dist,
                                           uint32_t* mcnt, uint32_t* lock, uint32_t BUFM, uint32_t k,
@@ -99,7 +89,7 @@ __device__ __forceinline__ void mih_flush(uint64_t* mbuf, volatile uint64_t* tau
   const uint64_t ntau = topk_compact(mbuf, mcnt, BUFM, k, lane, 32, WarpSync());
   if (lane == 0) {
     *tau_key = ntau;
-    *tau_dist = ntau == kEmptyKey ? kInfDist : (uint32_t)(ntau >> 32);
+    if (ntau != kEmptyKey) atomicMin((uint32_t*)tau_dist, (uint32_t)(ntau >> 32));
     __threadfence_block();
     atomicExch(lock, 0u);
   }
@@ -108,7 +98,7 @@ __device__ __forceinline__ void mih_flush(uint64_t* mbuf, volatile uint64_t* tau
 }
 
 template <int W, bool APPROX>
-__global__ void __launch_bounds__(kMihThreads) mih_search_kernel(const MihParams p) {
+__global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* mbuf = (uint64_t*)smem_raw;
   uint64_t* wbuf_all = mbuf + p.BUFM;
@@ -118,6 +108,7 @@ __global__ void __launch_bounds__(kMihThreads) mih_search_kernel(const MihParams
   __shared__ uint32_t s_qkey[kMaxTables];
   __shared__ unsigned long long s_probes, s_occ, s_cands, s_unique;
   __shared__ TableDev s_tab[kMaxTables];
+  __shared__ uint32_t s_hist[64 * W + 32];      // distances of the distinct candidates that passed the threshold
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t q = blockIdx.x;
@@ -125,6 +116,7 @@ __global__ void __launch_bounds__(kMihThreads) mih_search_kernel(const MihParams
 
   if (tid < 2 * W) s_q[tid] = p.queries[(size_t)q * 2 * W + tid];
   if (tid < m) s_tab[tid] = p.tables[tid];
+  for (uint32_t i = tid; i < 64 * W + 32; i += kMihThreads) s_hist[i] = 0;
   if (tid == 0) {
     s_tau_key = kEmptyKey; s_tau_dist = kInfDist; s_mcnt = 0; s_lock = 0; s_stop = 0;
     s_probes = 0; s_occ = 0; s_cands = 0; s_unique = 0;
@@ -170,63 +162,96 @@ __global__ void __launch_bounds__(kMihThreads) mih_search_kernel(const MihParams
         const uint32_t len = __shfl_sync(0xffffffffu, blen, src);
         const uint64_t* bc = s_tab[t].codes;
         const uint32_t* bi = s_tab[t].ids;
-        // 16-byte units: W == 1 -> two codes per unit (unit u = codes 2u, 2u+1), else W/2 units per code
-        constexpr int CPL = W == 1 ? 2 : 1;                 // codes per lane per load group
+        // 16-byte units: W == 1 -> two codes per unit (unit = codes 2u, 2u+1), else W/2 units per code.
+        // Each lane keeps U independent 128-bit loads in flight per iteration.
+        constexpr int CPL = W == 1 ? 2 : 1;                 // codes per 128-bit group
+        constexpr int UPC = W == 1 ? 1 : W / 2;             // 128-bit loads per group
+        constexpr int U = W == 4 ? 2 : 4;                   // groups per lane per iteration
         const uint32_t first = W == 1 ? (start & ~1u) : start;
         const uint32_t last = start + len;                  // exclusive
-        for (uint32_t j0 = first; j0 < last; j0 += 32 * CPL) {
-          const uint32_t j = j0 + lane * CPL;
-          uint32_t cw[CPL][2 * W];
-          if (j < last) {
-            const uint4* src4 = reinterpret_cast<const uint4*>(bc + (size_t)j * W);
-            if constexpr (W == 1) {
-              const uint4 v = ld_stream_u4(src4);
-              cw[0][0] = v.x; cw[0][1] = v.y; cw[1][0] = v.z; cw[1][1] = v.w;
-            } else {
+        for (uint32_t j0 = first; j0 < last; j0 += 32 * CPL * U) {
+          uint32_t cw[U][CPL][2 * W];
 #pragma unroll
-              for (int u = 0; u < W / 2; ++u) {
-                const uint4 v = ld_stream_u4(src4 + u);
-                cw[0][4 * u] = v.x; cw[0][4 * u + 1] = v.y; cw[0][4 * u + 2] = v.z; cw[0][4 * u + 3] = v.w;
+          for (int u = 0; u < U; ++u) {
+            const uint32_t j = j0 + (u * 32 + lane) * CPL;
+            if (j < last) {
+              const uint4* src4 = reinterpret_cast<const uint4*>(bc + (size_t)j * W);
+              if constexpr (W == 1) {
+                const uint4 v = ld_stream_u4(src4);
+                cw[u][0][0] = v.x; cw[u][0][1] = v.y; cw[u][1][0] = v.z; cw[u][1][1] = v.w;
+              } else {
+#pragma unroll
+                for (int h = 0; h < UPC; ++h) {
+                  const uint4 v = ld_stream_u4(src4 + h);
+                  cw[u][0][4 * h] = v.x; cw[u][0][4 * h + 1] = v.y; cw[u][0][4 * h + 2] = v.z; cw[u][0][4 * h + 3] = v.w;
+                }
               }
             }
           }
           const uint32_t tau = *v_tau_dist;
+          uint32_t dd[U][CPL];
+          uint32_t mn = kInfDist;
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            const uint32_t jj = j + c;
-            const bool in = jj >= start && jj < last;
-            uint32_t d = kInfDist;
-            if (in) d = hamming_exact<W>(cw[c], qw);                             // :253 compute_hamming_dist
-            bool pass = in && d <= tau;
-            bool first_seen = true;
-            if (APPROX ? in : pass) {
-              // first-discoverer test: emitted only by the lowest table among those whose substring
-              // distance equals the minimum (which is `radius` for table t at this step)
-              uint32_t x[2 * W];
+          for (int u = 0; u < U; ++u)
 #pragma unroll
-              for (int i = 0; i < 2 * W; ++i) x[i] = cw[c][i] ^ qw[i];
-              for (uint32_t t2 = 0; t2 < m; ++t2) {
-                if (t2 == t) continue;
-                const uint32_t sd = __popc(substring<W>(x, t2, sbits));
-                if (sd < radius || (sd == radius && t2 < t)) { first_seen = false; break; }
+            for (int c = 0; c < CPL; ++c) {
+              const uint32_t jj = j0 + (u * 32 + lane) * CPL + c;
+              const bool in = jj >= start && jj < last;
+              dd[u][c] = in ? hamming_exact<W>(cw[u][c], qw) : kInfDist;          // :253 compute_hamming_dist
+              mn = min(mn, dd[u][c]);
+            }
+          // common case: nothing in this stretch beats the current k-th distance
+          if (!__any_sync(0xffffffffu, APPROX ? mn != kInfDist : mn <= tau)) continue;
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+              const uint32_t jj = j0 + (u * 32 + lane) * CPL + c;
+              const uint32_t d = dd[u][c];
+              const bool in = d != kInfDist;
+              bool pass = in && d <= tau;
+              if (APPROX ? in : pass) {
+                // first-discoverer test: emitted only by the lowest table among those whose substring
+                // distance equals the minimum (which is `radius` for table t at this step)
+                bool first_seen = true;
+                uint32_t x[2 * W];
+#pragma unroll
+                for (int i = 0; i < 2 * W; ++i) x[i] = cw[u][c][i] ^ qw[i];
+                for (uint32_t t2 = 0; t2 < m; ++t2) {
+                  if (t2 == t) continue;
+                  const uint32_t sd = __popc(substring<W>(x, t2, sbits));
+                  if (sd < radius || (sd == radius && t2 < t)) { first_seen = false; break; }
+                }
+                if (APPROX && first_seen) ++my_unique;
+                pass = pass && first_seen;
               }
-              if (APPROX && first_seen) ++my_unique;
-              pass = pass && first_seen;
+              uint64_t key = 0;
+              if (pass) {
+                key = pack_key(d, bi[jj]);
+                pass = key < *v_tau_key;
+              }
+              if (pass) {
+                // exact running threshold: count the distance, lower tau once k codes are closer
+                atomicAdd(&s_hist[d], 1u);
+                const uint32_t tnow = *v_tau_dist;
+                if (d < tnow) {
+                  uint32_t cum = 0;
+                  const uint32_t lim = min(tnow, (uint32_t)(64 * W + 1));
+                  for (uint32_t b2 = 0; b2 < lim; ++b2) {
+                    cum += *(volatile uint32_t*)&s_hist[b2];
+                    if (cum >= k) { atomicMin((uint32_t*)&s_tau_dist, b2); break; }
+                  }
+                }
+              }
+              const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+              if (mask) {
+                if (wcnt + 32 > kMihWbuf)
+                  mih_flush(mbuf, v_tau_key, v_tau_dist, &s_mcnt, &s_lock, p.BUFM, k, wbuf, wcnt, lane);
+                if (pass) wbuf[wcnt + __popc(mask & ((1u << lane) - 1))] = key;
+                wcnt += __popc(mask);
+                __syncwarp();
+              }
             }
-            uint64_t key = 0;
-            if (pass) {
-              key = pack_key(d, bi[jj]);
-              pass = key < *v_tau_key;
-            }
-            const uint32_t mask = __ballot_sync(0xffffffffu, pass);
-            if (mask) {
-              if (wcnt + 32 > kMihWbuf)
-                mih_flush(mbuf, v_tau_key, v_tau_dist, &s_mcnt, &s_lock, p.BUFM, k, wbuf, wcnt, lane);
-              if (pass) wbuf[wcnt + __popc(mask & ((1u << lane) - 1))] = key;
-              wcnt += __popc(mask);
-              __syncwarp();
-            }
-          }
         }
       }
     }

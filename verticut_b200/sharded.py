@@ -33,11 +33,12 @@ def gather_layout(world_size, nq, k):
 class ShardedSearcher:
     """One rank's view of the sharded database.
 
-    `index` is this rank's capi.Index (first_id = start of its id range).  `merge_fn(gathered, k)` is
-    injectable for CPU tests of the plumbing; by default the CUDA merge kernel is used.
+    `index` is this rank's capi.Index (first_id = start of its id range).  The two device steps are methods so
+    that the host-side plumbing (shard ranges, gather layout, collective) can be exercised on CPU with the
+    `gloo` backend by overriding them; the product path always runs the CUDA kernels.
     """
 
-    def __init__(self, index, group=None, merge_fn=None):
+    def __init__(self, index, group=None):
         import torch
         import torch.distributed as dist
 
@@ -46,7 +47,6 @@ class ShardedSearcher:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.merge_fn = merge_fn
         self._bufs = {}
 
     def _buffers(self, nq, k, device):
@@ -59,30 +59,35 @@ class ShardedSearcher:
             self._bufs[key] = (local, gathered, merged)
         return self._bufs[key]
 
-    def search(self, d_queries, k, mode="mih", approximate=False, max_radius=-1):
-        """d_queries: uint8 tensor [nq, code_bytes] on this rank's GPU.  Returns an int64 tensor [nq, k] of
-        packed words (bit pattern of uint64, ascending), identical on every rank."""
-        t = self.torch
+    def _stream(self, device):
+        return self.torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0
+
+    # ---- device steps (CUDA kernels through the C ABI) --------------------------------------------------
+    def local_search(self, d_queries, k, mode, approximate, max_radius, out_keys):
         nq = d_queries.shape[0]
-        local, gathered, merged = self._buffers(nq, k, d_queries.device)
-        stream = t.cuda.current_stream().cuda_stream
+        stream = self._stream(d_queries.device)
         if mode == "mih":
-            self.index.search_mih_dev(d_queries.data_ptr(), nq, k, local.data_ptr(), approximate=approximate,
+            self.index.search_mih_dev(d_queries.data_ptr(), nq, k, out_keys.data_ptr(), approximate=approximate,
                                       max_radius=max_radius, stream=stream)
         elif mode == "linear":
-            self.index.search_linear_dev(d_queries.data_ptr(), nq, k, local.data_ptr(), stream=stream)
+            self.index.search_linear_dev(d_queries.data_ptr(), nq, k, out_keys.data_ptr(), stream=stream)
         else:
             raise ValueError("mode must be 'mih' or 'linear'")
+
+    def merge(self, gathered, k, out_keys):
+        n_lists, nq, _ = gathered.shape
+        capi.merge_topk_dev(self.index.device, gathered.data_ptr(), n_lists, nq, k, out_keys.data_ptr(),
+                            stream=self._stream(gathered.device))
+
+    # ---- the batch -----------------------------------------------------------------------------------------
+    def search(self, d_queries, k, mode="mih", approximate=False, max_radius=-1):
+        """d_queries: uint8 tensor [nq, code_bytes] on this rank's device.  Returns an int64 tensor [nq, k] of
+        packed words (bit pattern of uint64, ascending), identical on every rank."""
+        nq = d_queries.shape[0]
+        local, gathered, merged = self._buffers(nq, k, d_queries.device)
+        self.local_search(d_queries, k, mode, approximate, max_radius, local)
         if self.world == 1:
             return local
         self.dist.all_gather_into_tensor(gathered.view(-1), local.view(-1), group=self.group)
-        if self.merge_fn is not None:
-            return self.merge_fn(gathered, k)
-        capi.merge_topk_dev(self.index.device, gathered.data_ptr(), self.world, nq, k, merged.data_ptr(), stream=stream)
+        self.merge(gathered, k, merged)
         return merged
-
-
-def merge_gathered_host(gathered, k):
-    """Plumbing-test helper: the same fold on host arrays through the library's host-buffer merge."""
-    arr = np.ascontiguousarray(gathered, dtype=np.uint64)
-    return capi.merge_topk(0, arr, k)
