@@ -1,0 +1,69 @@
+"""The C++ host mirror (GpuTableProxy : BaseProxy, SearchWorker, the reference-style CLIs) end to end on the GPU:
+raw code / query files in the reference's format, stdout in the reference's formats, results vs the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "verticut_b200", "host", "bin")
+
+
+def _files(tmp_path, oracle, n, bits, nq):
+    codes = oracle.synth_codes(12345, 0, n, bits // 8)
+    queries = oracle.synth_codes(67890, 0, nq, bits // 8)
+    cf, qf = tmp_path / "lsh.code", tmp_path / "query.code"
+    cf.write_bytes(codes.tobytes())
+    qf.write_bytes(queries.tobytes())
+    return codes, queries, str(cf), str(qf)
+
+
+def _run(args):
+    res = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    return res.stdout
+
+
+@pytest.mark.parametrize("bits,m", [(64, 4), (128, 8)])
+def test_cli_mih_matches_oracle(tmp_path, oracle, bits, m):
+    n, nq, k = 30_000, 5, 10
+    codes, queries, cf, qf = _files(tmp_path, oracle, n, bits, nq)
+    out = _run([os.path.join(BIN, "image-search"), "mih", "-s", "gpu", "-f", cf, "-q", qf, "-b", str(bits), "-n", str(m), "-k", str(k)])
+    oid, od, oc = oracle.linear_search(codes, queries, k)
+    blocks = re.split(r"query \d+\n", out)[1:]
+    assert len(blocks) == nq
+    for q, blk in enumerate(blocks):
+        pairs = [(int(a), int(b)) for a, b in re.findall(r"^(\d+) : (\d+)$", blk, flags=re.M)]
+        assert pairs == list(zip(oid[q][::-1].tolist(), od[q][::-1].tolist()))      # descending distance, as the reference prints
+    assert "n_sub_reads" in out and "radius" in out and "-------Timings-------" in out
+
+
+def test_cli_linear_and_accuracy_and_integrity(tmp_path, oracle):
+    n, nq, k = 20_000, 3, 10
+    codes, queries, cf, qf = _files(tmp_path, oracle, n, 64, nq)
+    out = _run([os.path.join(BIN, "image-search"), "linear", "-f", cf, "-q", qf, "-b", "64", "-n", "4", "-k", str(k)])
+    got = [(int(a), int(b)) for a, b in re.findall(r"Find image with id=(\d+) and hamming_dist=(\d+)", out)]
+    oid, od, oc = oracle.linear_search(codes, queries, k)
+    want = []
+    for q in range(nq):
+        want += list(zip(oid[q][::-1].tolist(), od[q][::-1].tolist()))
+    assert got == want
+    out = _run([os.path.join(BIN, "image-search"), "accuracy", "-f", cf, "-q", qf, "-b", "64", "-n", "4", "-k", str(k)])
+    rows = [ln.split() for ln in out.splitlines() if re.match(r"^[\d.]+ [\d.]+ [\d.]+$", ln)]
+    assert len(rows) == nq and all(float(r[1]) >= float(r[0]) for r in rows)    # approximate is never better than exact
+    out = _run([os.path.join(BIN, "image-search"), "integrity", "-f", cf, "-b", "64", "-n", "4"])
+    assert "%d images, 0 errors" % n in out
+
+
+def test_build_tables_via_baseproxy_put(tmp_path, oracle):
+    # the reference's build loop (get -> append -> put per code and table) against GpuTableProxy, then the
+    # reference's integrity check through BaseProxy::get
+    n = 1500
+    codes, _, cf, _ = _files(tmp_path, oracle, n, 64, 1)
+    out = _run([os.path.join(BIN, "build-tables"), "--via-put", "--check", "-f", cf, "-b", "64", "-n", "4"])
+    assert "images : %d" % n in out and "%d images, 0 errors" % n in out
+    out = _run([os.path.join(BIN, "build-tables"), "--check", "-f", cf, "-b", "64", "-n", "4"])
+    assert "%d images, 0 errors" % n in out

@@ -1,0 +1,95 @@
+// distributed-image-search / linear-search / accuracy-test / integrity-check for --server gpu, one binary:
+//   image-search mih       -f codes -q queries [-b bits] [-n tables] [-k knn] [-a] [-i max images]
+//   image-search linear    -f codes -q queries ...
+//   image-search accuracy  -f codes -q queries ...      (reference: src/accuracy_test.cc)
+//   image-search integrity -f codes ...                 (reference: src/integrity_check.cc)
+// Output formats follow the reference: result lines "id : dist" (what image_search_server.cc:94 parses), the
+// averaged statistics line of src/distributed_image_search.cc:87-93, and for the scan
+// "Find image with id=%d and hamming_dist=%d" (src/linear_search.cc:62).  Neighbours are listed in descending
+// distance, as the reference does.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+
+#include <iostream>
+#include <vector>
+
+#include "args_config.h"
+#include "gpu_search_worker.h"
+#include "integrity.h"
+
+static double now() { timeval t; gettimeofday(&t, 0); return t.tv_sec + t.tv_usec * 1e-6; }
+
+static std::vector<char> read_queries(const char* path, int rec, int limit) {
+  std::vector<char> q;
+  FILE* f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "Couldn't open file %s\n", path); exit(1); }
+  std::vector<char> one(rec);
+  while ((int)(q.size() / rec) < limit && fread(one.data(), rec, 1, f) == 1) q.insert(q.end(), one.begin(), one.end());
+  fclose(f);
+  return q;
+}
+
+int main(int argc, char* argv[]) {
+  if (argc < 2) usage();
+  const char* mode = argv[1];
+  configure(argc - 1, argv + 1);
+  const int rec = binary_bits / 8;
+  const bool linear = !strcmp(mode, "linear");
+  GpuTableProxy proxy(binary_bits, linear ? 0 : n_tables);
+  double t0 = now();
+  if (proxy.init(config_path) != 0) { fprintf(stderr, "proxy init failed: %s\n", proxy.last_error()); return 1; }
+  if (proxy.load_code_file(binary_file, (uint64_t)image_total) != 0) { fprintf(stderr, "Can't open file %s.\n", binary_file); return 1; }
+  if (proxy.finalize() != 0) { fprintf(stderr, "build failed: %s\n", proxy.last_error()); return 1; }
+  double t_connect = now() - t0;
+  if (!strcmp(mode, "integrity")) return run_integrity(&proxy);
+  if (!query_file) { fprintf(stderr, "a query file is required (-q)\n"); return 1; }
+  std::vector<char> queries = read_queries(query_file, rec, max_queries);
+  const size_t nq = queries.size() / rec;
+  SearchWorker worker(&proxy, (int)proxy.size());
+  typedef std::list<SearchWorker::search_result_st> Result;
+  double t1 = now();
+  if (linear) {
+    for (size_t q = 0; q < nq; ++q) {
+      Result r = worker.linear_find(&queries[q * rec], rec, knn);
+      for (Result::iterator it = r.begin(); it != r.end(); ++it)
+        printf("Find image with id=%d and hamming_dist=%d\n", it->image_id, it->dist);
+    }
+  } else if (!strcmp(mode, "mih")) {
+    std::vector<Result> res = worker.find_batch(queries.data(), rec, nq, knn, approximate != 0);
+    uint64_t sub = 0, local = 0, radius = 0;
+    for (size_t q = 0; q < nq; ++q) {
+      printf("query %zu\n", q);
+      for (Result::iterator it = res[q].begin(); it != res[q].end(); ++it) std::cout << it->image_id << " : " << it->dist << std::endl;
+      sub += worker.batch_stats()[q].probes; local += worker.batch_stats()[q].occupancy_tests; radius += worker.batch_stats()[q].radius;
+    }
+    if (nq) {
+      std::cout << "Averate result : " << std::endl;     // sic, src/distributed_image_search.cc:88
+      std::cout << 0 << "  n_main_reads : " << 0 << " , n_sub_reads : " << sub / nq << ", n_local_reads : " << local / nq
+                << ", radius : " << radius / nq << ", rdma : " << 0 << std::endl;
+    }
+  } else if (!strcmp(mode, "accuracy")) {
+    // approximate vs exact: mean distance of both and the count of approximate results that are worse than
+    // the exact farthest one (src/accuracy_test.cc:106-135)
+    uint64_t total_ex = 0, total_app = 0, inaccurate = 0;
+    std::vector<Result> app = worker.find_batch(queries.data(), rec, nq, knn, true);
+    std::vector<Result> ex = worker.find_batch(queries.data(), rec, nq, knn, false);
+    for (size_t q = 0; q < nq; ++q) {
+      for (Result::iterator it = ex[q].begin(); it != ex[q].end(); ++it) total_ex += it->dist;
+      for (Result::iterator it = app[q].begin(); it != app[q].end(); ++it) total_app += it->dist;
+      const uint32_t threshold = ex[q].empty() ? 0 : ex[q].front().dist;
+      for (Result::iterator it = app[q].begin(); it != app[q].end() && it->dist > threshold; ++it) ++inaccurate;
+      std::cout << (float)total_ex / (q + 1) / knn << " " << (float)total_app / (q + 1) / knn << " " << (float)inaccurate / (q + 1) / knn << std::endl;
+    }
+  } else {
+    usage();
+  }
+  double t_while = now() - t1;
+  std::cout << "-------Timings-------" << std::endl;      // src/timer.h:31-36
+  std::cout << "connect : " << t_connect << " s" << std::endl;
+  std::cout << "while : " << t_while << " s" << std::endl;
+  std::cout << "---------------------" << std::endl;
+  proxy.close();
+  return 0;
+}
