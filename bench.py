@@ -145,7 +145,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_total = int(os.environ.get("VC_BENCH_N", 1_000_000_000))
-    Q = int(os.environ.get("VC_BENCH_Q", 1024))
+    Q = int(os.environ.get("VC_BENCH_Q", 4096))
     mode = os.environ.get("VC_BENCH_MODE", "mih")
     nbytes = CODE_BITS // 8
 
@@ -222,21 +222,39 @@ def main():
     stats_t = torch.zeros((Q, capi.STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     keys_t = torch.empty((Q, K_NN), dtype=torch.int64, device=dev)
     roofline = None
+    integer_pipe = None
     if mode == "mih":
         ix.search_mih_dev(dev_batches[-1].data_ptr(), Q, K_NN, keys_t.data_ptr(), d_stats=stats_t.data_ptr(),
                           stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         st = stats_t.cpu().numpy().view(capi.STATS_DTYPE).reshape(-1)
         probes, cands = float(st["probes"].sum()), float(st["candidates"].sum())
-        algo_bytes = probes * 8 + cands * nbytes          # two 4-byte row_ptr reads per probe + the candidates' codes
+        batched = bool(ix.get_param("mih.last_batched"))
         k_s = float(np.mean(kernel_ns)) * 1e-9
+        per_query_bytes = probes * 8 + cands * nbytes     # what one-query-at-a-time MIH must move
+        if batched:
+            # bucket-stationary: every probed bucket is read once per radius level for all its queries
+            algo_bytes = float(ix.get_param("mih.last_bucket_codes")) * nbytes + probes * 8
+            kernel = "bmih_verify_kernel (sum over radius levels)"
+        else:
+            algo_bytes = per_query_bytes
+            kernel = "mih_search_kernel"
         achieved = algo_bytes / k_s / 1e9
-        roofline = {"bound": "hbm", "kernel": "mih_search_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": k_s * 1e3,
                     "probes_per_query": probes / Q, "candidates_per_query": cands / Q,
                     "mean_radius": float(st["radius"].mean()),
+                    "per_query_formula_GBps": per_query_bytes / k_s / 1e9,
                     "survey_formula_GBps": (probes * 8 + cands * (4 + nbytes)) / k_s / 1e9}
+        sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        n_sms = ix.get_param("num_sms")
+        pairs_s = cands / k_s
+        integer_pipe = {"what": "code-query distance tests by the dominant kernel; it is POPC-bound when batched",
+                        "pairs_per_s": pairs_s, "pairs_per_clk_per_sm": pairs_s / n_sms / sm_clk,
+                        "popc_peak_per_clk_per_sm": 15.4, "popc_per_pair": 1 if nbytes <= 16 else nbytes // 4,
+                        "frac_of_popc_peak": pairs_s / n_sms / sm_clk / 15.4 * (1 if nbytes <= 16 else nbytes // 4),
+                        "peak_source": "tools/microbench.cu on this B200: 15.4 POPC/clk/SM"}
 
     # ---- e2e: host buffers through the C ABI (N = 1) or pinned -> device -> search -> merged -> host (N > 1) ----
     e2e_steps = max(3, min(args.steps, 5))
@@ -326,7 +344,7 @@ def main():
                        "mode": mode, "batch": Q, "n_codes": n_total, "codes_per_gpu": e - b,
                        "l2": "inputs larger than L2 (tables %.1f GB per GPU, >= 300 MB touched per query)" % (ix.info()["device_bytes"] / 1e9),
                        "parallelism": "id-shard x%d, NCCL all-gather top-k merge" % world},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "integer_pipe": integer_pipe, "cpu_baseline": cpu_baseline,
             "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
         }
         print(json.dumps(line))

@@ -1,0 +1,59 @@
+"""The bucket-stationary batched MIH path (bmih.cuh) must give exactly the answers and statistics of the
+per-query kernel: the whole MIH parity suite is re-run with the batched path forced on, plus batch-sized cases."""
+import numpy as np
+import pytest
+
+import test_gpu_mih as base
+from verticut_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _force_batched():
+    base.BATCHED = 1
+    yield
+    base.BATCHED = 0
+
+
+@pytest.mark.parametrize("n,bits,m,nq,k", [
+    (20_000, 64, 4, 16, 10), (200_000, 64, 4, 8, 100), (50_000, 128, 8, 6, 100), (20_000, 64, 8, 5, 10), (5_000, 256, 16, 3, 50),
+])
+def test_batched_exact_equals_linear_scan(oracle, n, bits, m, nq, k):
+    base._check_exact(oracle, n, bits, m, nq, k)
+
+
+def test_batched_first_id_small_and_large_k(oracle):
+    base._check_exact(oracle, 30_000, 64, 4, 5, 100, first_id=3_000_000_000)
+    base._check_exact(oracle, 50, 64, 4, 3, 100)
+    base._check_exact(oracle, 20_000, 64, 4, 2, 1000)
+
+
+def test_batched_heavy_ties_fall_back_exactly(oracle):
+    base.test_mih_heavy_ties(oracle)
+
+
+@pytest.mark.parametrize("bits,m,r", [(64, 4, 0), (64, 4, 2), (128, 8, 1), (256, 16, 1)])
+def test_batched_fixed_radius(oracle, bits, m, r):
+    base.test_mih_fixed_radius(oracle, bits, m, r)
+
+
+def test_batched_large_batch_matches_per_query_kernel(oracle):
+    # a real batch: 300 queries over 2M codes (buckets of ~30 codes x 4 tables), both paths, all statistics
+    n, nq, k = 2_000_000, 300, 100
+    ix = capi.Index(64, 4)
+    ix.add_synthetic(n, 12345)
+    ix.build()
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    ix.set_param("mih.batched", 0)
+    a = ix.search_mih(queries, k)
+    ix.set_param("mih.batched", 1)
+    b = ix.search_mih(queries, k)
+    assert ix.get_param("mih.last_batched") == 1
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    for f in ("radius", "n_results", "probes", "candidates"):
+        np.testing.assert_array_equal(a[3][f], b[3][f])
+    lid, ld, lc = ix.search_linear(queries[:16], k)
+    np.testing.assert_array_equal(b[0][:16], lid)
+    ix.close()

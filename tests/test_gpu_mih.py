@@ -9,10 +9,14 @@ from verticut_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
+BATCHED = 0      # module switch: 1 forces the bucket-stationary batched path wherever it is legal (test_gpu_bmih.py)
+
+
 def _mk(oracle, n, bits, m, first_id=0, seed=12345):
     nbytes = bits // 8
     codes = oracle.synth_codes(seed, first_id, n, nbytes)
     ix = capi.Index(bits, m, first_id=first_id)
+    ix.set_param("mih.batched", BATCHED)
     ix.add(codes)
     ix.build()
     return codes, ix
@@ -121,6 +125,7 @@ def test_mih_heavy_ties(oracle):
     base = oracle.synth_codes(9, 0, 4, 8)
     codes = np.repeat(base, n // 4, axis=0)                # four distinct codes, 1250 copies each
     ix = capi.Index(64, 4)
+    ix.set_param("mih.batched", BATCHED)
     ix.add(codes)
     ix.build()
     queries = oracle.synth_codes(67890, 0, 6, 8)

@@ -15,6 +15,7 @@
 #include "build.cuh"
 #include "mih.cuh"
 #include "scan.cuh"
+#include "bmih.cuh"
 
 using namespace vc;
 
@@ -100,6 +101,7 @@ struct vc_index {
   size_t smem_optin = 0;
   // scratch
   DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small, d_gstate;
+  DevBuf b_state, b_buckets, b_qlist, b_items, b_keys0, b_stats0, b_redo;   // batched MIH
   PinBuf h_q, h_ids, h_dists, h_counts, h_stats, h_small;
   // knobs
   int64_t scan_prefilter = -1;    // -1 auto, 0 off, 1 on
@@ -110,10 +112,16 @@ struct vc_index {
   int64_t scan_interleave = 1;    // slices interleaved step-wise (1) or contiguous (0)
   int64_t scan_smem_kb = 0;       // 0 auto: shared memory budget per CTA for the query tile
   int64_t merge_fanin = 64;
+  int64_t mih_batched = -1;       // -1 auto, 0 per-query kernel only, 1 bucket-stationary batched path whenever legal
+  int64_t mih_prefilter = -1;
+  int64_t mih_cpi_steps = 0;
+  int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
   int64_t profile = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
+  cudaEvent_t lev[2 * 34] = {nullptr};   // batched MIH: one (start, stop) pair per radius level around the verify kernel
+  int lev_used = 0;                        // > 0: last search was batched, sum these pairs
   // counters
   int64_t launches = 0;           // kernels launched by this index since creation
   int64_t last_scan_grid = 0, last_scan_qt = 0, last_scan_slices = 0, last_scan_smem = 0, last_scan_occ = 0, last_scan_stages = 0;
@@ -196,7 +204,9 @@ void vc_index_destroy(vc_index* ix) {
   if (ix->d_tab) cudaFree(ix->d_tab);
   if (ix->d_codes) cudaFree(ix->d_codes);
   if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
-  DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate};
+  for (cudaEvent_t e : ix->lev) if (e) cudaEventDestroy(e);
+  DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate,
+                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_keys0, &ix->b_stats0, &ix->b_redo};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
   for (PinBuf* b : pb) b->release();
@@ -517,7 +527,7 @@ static int launch_scan(vc_index* ix, const ScanParams& p, size_t smem, cudaStrea
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
   if (ix->profile) cudaEventRecord(ix->ev0, st);
   kern<<<p.n_qtiles * p.n_slices, kScanCtaThreads, smem, st>>>(p);
-  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; }
+  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
   ix->launches++;
   CU(cudaGetLastError());
   return VC_OK;
@@ -633,9 +643,170 @@ static int launch_mih(vc_index* ix, const MihParams& p, cudaStream_t st) {
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   if (ix->profile) cudaEventRecord(ix->ev0, st);
   kern<<<p.nq, kMihThreads, smem, st>>>(p);
-  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; }
+  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
   ix->launches++;
   CU(cudaGetLastError());
+  return VC_OK;
+}
+
+extern "C" {
+
+}  // extern "C"
+
+static int mih_per_query(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                         uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
+  MihParams p;
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = ix->m; p.sbits = ix->sbits;
+  p.BUFM = pow2_at_least(k + kMihWbuf);
+  p.approximate = approximate; p.max_radius = max_radius;
+  p.tables = ix->d_tab; p.out_keys = d_out_keys; p.stats = d_stats;
+  const bool ap = approximate != 0 && max_radius < 0;
+  if (ix->W == 1) return ap ? launch_mih<1, true>(ix, p, st) : launch_mih<1, false>(ix, p, st);
+  if (ix->W == 2) return ap ? launch_mih<2, true>(ix, p, st) : launch_mih<2, false>(ix, p, st);
+  return ap ? launch_mih<4, true>(ix, p, st) : launch_mih<4, false>(ix, p, st);
+}
+
+static uint64_t host_binom(uint32_t n, uint32_t r) {
+  if (r > n) return 0;
+  uint64_t c = 1;
+  for (uint32_t i = 1; i <= r; ++i) c = c * (n - r + i) / i;
+  return c;
+}
+
+// exclusive scan of up to 2048 * 2048 u32 in place, no allocation (sums: >= ceil(n / 2048) words)
+static int scan_inplace_small(vc_index* ix, uint32_t* d, uint64_t n, uint32_t* sums, cudaStream_t st) {
+  const uint64_t nb = (n + kScanTile - 1) / kScanTile;
+  if (nb > (uint64_t)kScanTile) return fail(VC_ERR_ARG, "scan too large");
+  if (nb <= 1) { scan_apply_kernel<<<1, kBuildThreads, 0, st>>>(d, n, nullptr, d); ix->launches++; return VC_OK; }
+  scan_reduce_kernel<<<(unsigned)nb, kBuildThreads, 0, st>>>(d, n, sums);
+  scan_apply_kernel<<<1, kBuildThreads, 0, st>>>(sums, nb, nullptr, sums);
+  scan_apply_kernel<<<(unsigned)nb, kBuildThreads, 0, st>>>(d, n, sums, d);
+  ix->launches += 3;
+  return VC_OK;
+}
+
+// Bucket-stationary batched MIH (bmih.cuh).  Exact or fixed-radius search over dense tables.
+template <int W>
+static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int max_radius,
+                       uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
+  using Cfg = BmihCfg<W>;
+  const uint32_t m = ix->m, sbits = ix->sbits, n_buckets = m << sbits;
+  int rc;
+  // ---- workspace ---------------------------------------------------------------------------------------
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
+               o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
+               o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
+               o_ctr = take(64);
+  if ((rc = ix->b_state.ensure(off))) return rc;
+  if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024))) return rc;
+  if ((rc = ix->b_keys0.ensure((size_t)nq * k * 8))) return rc;
+  if ((rc = ix->b_stats0.ensure((size_t)nq * sizeof(vc_query_stats)))) return rc;
+  unsigned char* sb = (unsigned char*)ix->b_state.p;
+  uint32_t* ctr = (uint32_t*)(sb + o_ctr);            // [0] n_items  [1] item_cursor  [2] n_next  [3] any_overflow
+  BmihParams p;
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = m; p.sbits = sbits; p.radius = 0; p.max_radius = max_radius;
+  p.tables = ix->d_tab; p.active = nullptr; p.n_active = 0;
+  {
+    // work-item length: about one average bucket, between 2 and 8 CTA steps
+    const uint64_t avg = (ix->n >> sbits) + 1;
+    const uint64_t steps = std::min<uint64_t>(8, std::max<uint64_t>(2, (avg + Cfg::STEP - 1) / Cfg::STEP));
+    p.cpi = ix->mih_cpi_steps > 0 ? (uint32_t)ix->mih_cpi_steps * Cfg::STEP : (uint32_t)steps * Cfg::STEP;
+  }
+  p.bcount = (uint32_t*)ix->b_buckets.p; p.boffs = p.bcount + n_buckets;
+  uint32_t* scan_sums = p.boffs + n_buckets + 1 + 3;
+  p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
+  p.bucket_codes = (unsigned long long*)(ctr + 8);
+  p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
+  p.gtau = (uint32_t*)(sb + o_tau); p.ghist = (uint32_t*)(sb + o_hist); p.gflag = (uint32_t*)(sb + o_flag);
+  p.gradius = (uint32_t*)(sb + o_rad); p.gprobes = (unsigned long long*)(sb + o_probes); p.gcands = (unsigned long long*)(sb + o_cands);
+  uint32_t* actA = (uint32_t*)(sb + o_actA);
+  uint32_t* actB = (uint32_t*)(sb + o_actB);
+
+  // ---- level 0: the query's own buckets, by the per-query kernel (bounded memory while tau is unknown) ----
+  uint64_t* keys0 = (uint64_t*)ix->b_keys0.p;
+  vc_query_stats* stats0 = (vc_query_stats*)ix->b_stats0.p;
+  if ((rc = mih_per_query(ix, d_queries, nq, k, 0, 0, keys0, stats0, st))) return rc;
+  CU(cudaMemsetAsync(ctr, 0, 64, st));
+  bmih_init_kernel<<<nq, 128, 0, st>>>(p, keys0, stats0, Cfg::HB);
+  p.next_active = actA;
+  bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, nullptr, nq, 0, ctr + 3);
+  ix->launches += 2;
+  uint32_t h_ctr[4];
+  CU(cudaMemcpyAsync(h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  uint32_t n_active = h_ctr[2];
+  uint32_t* cur = actA;
+  uint32_t* nxt = actB;
+  const bool pf = ix->mih_prefilter < 0 ? (W <= 2) : ix->mih_prefilter != 0;
+  int occ = 1;
+  if (pf) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, true>, kBmihThreads, 0));
+  else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, false>, kBmihThreads, 0));
+  const int verify_grid = std::max(1, occ) * ix->num_sms;
+  int levels = 0;
+  int64_t items_total = 0;
+  bool first_verify = true;
+  for (uint32_t r = 1; n_active > 0 && r <= sbits; ++r) {
+    p.radius = r; p.active = cur; p.n_active = n_active; p.next_active = nxt;
+    const uint64_t total_probes = (uint64_t)n_active * m * host_binom(sbits, r);
+    if ((rc = ix->b_qlist.ensure(std::max<uint64_t>(total_probes, 1) * 4))) return rc;
+    p.qlist = (uint32_t*)ix->b_qlist.p;
+    const int pgrid = grid_for(total_probes, 256, ix->num_sms);
+    CU(cudaMemsetAsync(p.bcount, 0, (size_t)n_buckets * 4, st));
+    bmih_probe_kernel<W><<<pgrid, 256, 0, st>>>(p, 0);
+    CU(cudaMemcpyAsync(p.boffs, p.bcount, (size_t)n_buckets * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(p.boffs + n_buckets, 0, 4, st));
+    if ((rc = scan_inplace_small(ix, p.boffs, (uint64_t)n_buckets + 1, scan_sums, st))) return rc;
+    CU(cudaMemsetAsync(p.bcount, 0, (size_t)n_buckets * 4, st));
+    bmih_probe_kernel<W><<<pgrid, 256, 0, st>>>(p, 1);
+    CU(cudaMemsetAsync(ctr, 0, 12, st));
+    const int igrid = grid_for(n_buckets, 256, ix->num_sms);
+    bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 0);
+    CU(cudaMemcpyAsync(h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t n_items = h_ctr[0];
+    if ((rc = ix->b_items.ensure(std::max<size_t>(n_items, 1) * sizeof(BmihItem)))) return rc;
+    p.items = (BmihItem*)ix->b_items.p;
+    CU(cudaMemsetAsync(ctr, 0, 12, st));
+    bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
+    const bool timed = ix->profile && levels < 34;
+    if (timed) {
+      if (!ix->lev[2 * levels]) { CU(cudaEventCreate(&ix->lev[2 * levels])); CU(cudaEventCreate(&ix->lev[2 * levels + 1])); }
+      cudaEventRecord(ix->lev[2 * levels], st);
+    }
+    if (pf) bmih_verify_kernel<W, true><<<verify_grid, kBmihThreads, 0, st>>>(p);
+    else bmih_verify_kernel<W, false><<<verify_grid, kBmihThreads, 0, st>>>(p);
+    if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
+    first_verify = false;
+    bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, 1, ctr + 3);
+    ix->launches += 6;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_active = h_ctr[2];
+    std::swap(cur, nxt);
+    ++levels;
+    items_total += n_items;
+  }
+  if (ix->profile) { ix->lev_used = std::min(levels, 34); ix->ev_valid = true; }
+  (void)first_verify;
+  bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, d_stats);
+  ix->launches++;
+  if (h_ctr[3]) {
+    // some candidate buffer overflowed (heavy ties): those queries take the per-query kernel's exact answer
+    if ((rc = ix->b_redo.ensure((size_t)nq * k * 8 + (size_t)nq * sizeof(vc_query_stats)))) return rc;
+    uint64_t* rk = (uint64_t*)ix->b_redo.p;
+    vc_query_stats* rs = (vc_query_stats*)(rk + (size_t)nq * k);
+    if ((rc = mih_per_query(ix, d_queries, nq, k, 0, max_radius, rk, rs, st))) return rc;
+    bmih_patch_kernel<<<nq, 128, 0, st>>>(p.gflag, k, rk, rs, d_out_keys, d_stats);
+    ix->launches++;
+  }
+  CU(cudaGetLastError());
+  unsigned long long h_bc = 0;
+  CU(cudaMemcpyAsync(&h_bc, p.bucket_codes, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ix->last_mih_batched = 1; ix->last_mih_levels = levels; ix->last_mih_items = items_total; ix->last_mih_bucket_codes = (int64_t)h_bc;
   return VC_OK;
 }
 
@@ -649,16 +820,18 @@ int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t
   if (!ix->built) return fail(VC_ERR_STATE, "tables are not built (call vc_index_build after adding codes)");
   if (nq == 0) return VC_OK;
   DeviceGuard g(ix->device);
-  MihParams p;
-  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = ix->m; p.sbits = ix->sbits;
-  p.BUFM = pow2_at_least(k + kMihWbuf);
-  p.approximate = approximate; p.max_radius = max_radius;
-  p.tables = ix->d_tab; p.out_keys = d_out_keys; p.stats = d_stats;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool ap = approximate != 0 && max_radius < 0;
-  if (ix->W == 1) return ap ? launch_mih<1, true>(ix, p, st) : launch_mih<1, false>(ix, p, st);
-  if (ix->W == 2) return ap ? launch_mih<2, true>(ix, p, st) : launch_mih<2, false>(ix, p, st);
-  return ap ? launch_mih<4, true>(ix, p, st) : launch_mih<4, false>(ix, p, st);
+  // Bucket-stationary batching pays when several queries share a bucket and buckets are long enough to
+  // fill a CTA step; it needs dense tables and no distinct-candidate count (approximate mode).
+  const bool legal = ix->sbits <= 16 && !(approximate != 0 && max_radius < 0) && k < (uint32_t)kBmihCap / 2;
+  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && nq >= 64 && (ix->n >> ix->sbits) >= 256);
+  ix->last_mih_batched = 0;
+  if (legal && want) {
+    if (ix->W == 1) return mih_batched<1>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
+    if (ix->W == 2) return mih_batched<2>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
+    return mih_batched<4>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
+  }
+  return mih_per_query(ix, d_queries, nq, k, approximate, max_radius, d_out_keys, d_stats, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,6 +896,9 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "scan.ctas_per_sm")) ix->scan_ctas_per_sm = value;
   else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
   else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
+  else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
+  else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
+  else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
   else if (!strcmp(name, "profile")) {
     DeviceGuard g(ix->device);
     if (value && !ix->ev0) { CU(cudaEventCreate(&ix->ev0)); CU(cudaEventCreate(&ix->ev1)); }
@@ -748,15 +924,30 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "scan.last_stages")) *value = ix->last_scan_stages;
   else if (!strcmp(name, "scan.stages")) *value = ix->scan_stages;
   else if (!strcmp(name, "num_sms")) *value = ix->num_sms;
+  else if (!strcmp(name, "mih.batched")) *value = ix->mih_batched;
+  else if (!strcmp(name, "mih.last_batched")) *value = ix->last_mih_batched;
+  else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;
+  else if (!strcmp(name, "mih.last_items")) *value = ix->last_mih_items;
+  else if (!strcmp(name, "mih.last_bucket_codes")) *value = ix->last_mih_bucket_codes;
   else if (!strcmp(name, "profile")) *value = ix->profile;
   else if (!strcmp(name, "last_kernel_ns")) {
     // device time of the dominant kernel (scan_topk / mih_search) of the last search; waits for it
     if (!ix->profile || !ix->ev_valid) return fail(VC_ERR_STATE, "profiling is off or no search has run");
     DeviceGuard g(ix->device);
     float ms = 0.f;
-    CU(cudaEventSynchronize(ix->ev1));
-    CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
-    *value = (int64_t)((double)ms * 1e6);
+    if (ix->lev_used > 0) {               // batched MIH: sum of the verify kernels of all levels
+      double tot = 0;
+      for (int l = 0; l < ix->lev_used; ++l) {
+        CU(cudaEventSynchronize(ix->lev[2 * l + 1]));
+        CU(cudaEventElapsedTime(&ms, ix->lev[2 * l], ix->lev[2 * l + 1]));
+        tot += ms;
+      }
+      *value = (int64_t)(tot * 1e6);
+    } else {
+      CU(cudaEventSynchronize(ix->ev1));
+      CU(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+      *value = (int64_t)((double)ms * 1e6);
+    }
   }
   else return fail(VC_ERR_ARG, "unknown parameter '%s'", name);
   return VC_OK;

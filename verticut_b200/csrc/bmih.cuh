@@ -1,0 +1,343 @@
+// Batched, bucket-stationary MIH (K2-K5 for a BATCH of queries): every probed bucket is read from HBM once
+// per radius level for all the queries that probe it, instead of once per query.
+//
+// Same algorithm and the same answers as mih_search_kernel (mih.cuh) / SearchWorker::find
+// (src/search_worker.cc:65-264); what changes is the loop order.  The reference walks query -> radius ->
+// table -> probe -> bucket members.  Here, per radius level r (all still-active queries together):
+//   1. bmih_probe_kernel   every (query, table, probe) of the level is unranked (enumerate_entry,
+//                          search_worker.cc:230-264); non-empty buckets are counted, then - second pass -
+//                          the query is written into its bucket's list (a counting sort by bucket);
+//   2. bmih_items_kernel   each probed bucket is cut into work items of <= kBmihCPI codes x <= kBmihQT queries;
+//   3. bmih_verify_kernel  persistent CTAs pull items; a CTA stages the item's queries in shared memory,
+//                          streams the bucket's codes through registers with 128-bit loads and tests every
+//                          code against every query (XOR + POPC + MIN, optional half-POPC prefilter) - the
+//                          full-code verification of search_worker.cc:249-257.  Survivors of the distance
+//                          threshold pass the first-discoverer de-duplication (knn_found_, :183-190, decided
+//                          from the code itself) and are appended to the query's global candidate buffer; the
+//                          threshold tau[q] is the exact running k-th distance (global histogram + atomicMin);
+//   4. bmih_settle_kernel  per query: sort the buffer, keep the k best (the heap of :192-197), apply the
+//                          strict m-aware stop rule (:201-207) and build the next active list.
+// Level 0 (the query's own bucket in every table) is done by mih_search_kernel with max_radius = 0, which
+// also bounds memory when nothing is known about the distances yet.  A query whose candidate buffer
+// overflows (adversarial ties) is re-run by the per-query kernel, so the result is exact whatever the data.
+#pragma once
+#include "mih.cuh"
+#include "scan.cuh"
+
+namespace vc {
+
+constexpr int kBmihThreads = 256;
+constexpr int kBmihQT = 32;          // queries per work item
+constexpr int kBmihCap = 4096;       // candidate-buffer entries per query
+constexpr int kBmihU4 = 4;           // 128-bit loads per thread per step
+
+template <int W> struct BmihCfg {
+  static constexpr int C = 2 * kBmihU4 / W;                 // codes per thread per step (8 / 4 / 2)
+  static constexpr int STEP = kBmihThreads * C;             // codes per CTA step
+  static constexpr int QS = (2 * W + 1 + 3) / 4 * 4;        // u32 per staged query: words, tau, pad
+  static constexpr int HB = 64 * W + 32;
+};
+
+struct BmihItem { uint32_t bucket, code_chunk, q_chunk; };
+
+struct BmihParams {
+  const uint32_t* queries;      // [nq][2W]
+  uint32_t nq, k, m, sbits;
+  uint32_t radius;              // level being processed
+  uint32_t cpi;                 // codes per work item (multiple of the step size)
+  int max_radius;
+  const TableDev* tables;       // [m]
+  // per-level probe structures
+  const uint32_t* active;       // [n_active] query indices
+  uint32_t n_active;
+  uint32_t* bcount;             // [m << sbits] queries per bucket (pass 0), then cursor (pass 1)
+  uint32_t* boffs;              // [(m << sbits) + 1] exclusive scan of bcount
+  uint32_t* qlist;              // [total probes] query index per (bucket, slot)
+  BmihItem* items;
+  uint32_t* n_items;            // [1]
+  unsigned long long* bucket_codes;   // [1] codes of all distinct probed buckets, summed over levels (traffic accounting)
+  uint32_t* item_cursor;        // [1]
+  // per-query state
+  uint64_t* gbuf;               // [nq][kBmihCap]
+  uint32_t* gcnt;               // [nq]
+  uint64_t* gtaukey;            // [nq]
+  uint32_t* gtau;               // [nq]
+  uint32_t* ghist;              // [nq][HB]
+  uint32_t* gflag;              // [nq] bit0 = buffer overflowed (redo with the per-query kernel), bit1 = finished
+  uint32_t* gradius;            // [nq] last radius searched
+  unsigned long long* gprobes;  // [nq]
+  unsigned long long* gcands;   // [nq]
+  uint32_t* next_active;        // [nq]
+  uint32_t* n_next;             // [1]
+};
+
+// ---- 1. probes of one level -------------------------------------------------------------------------------
+// pass 0: count queries per non-empty bucket (+ statistics); pass 1: write the query into its bucket's list
+template <int W>
+__global__ void bmih_probe_kernel(const BmihParams p, int pass) {
+  const uint32_t per_table = c_binom[p.sbits][p.radius];
+  const uint64_t per_q = (uint64_t)per_table * p.m;
+  const uint64_t total = per_q * p.n_active;
+  for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t a = (uint32_t)(it / per_q);
+    const uint32_t rem = (uint32_t)(it % per_q);
+    const uint32_t t = rem / per_table, pidx = rem % per_table;
+    const uint32_t q = p.active[a];
+    const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
+    const uint32_t key = qkey ^ unrank_mask(p.sbits, p.radius, pidx);
+    const uint32_t* rp = p.tables[t].row_ptr;
+    const uint32_t len = rp[key + 1] - rp[key];
+    const uint32_t b = (t << p.sbits) + key;
+    if (pass == 0) {
+      if (len) { atomicAdd(&p.bcount[b], 1u); atomicAdd(&p.gcands[q], (unsigned long long)len); }
+    } else if (len) {
+      const uint32_t slot = atomicAdd(&p.bcount[b], 1u);
+      p.qlist[p.boffs[b] + slot] = q;
+    }
+  }
+}
+
+// ---- 2. work items -------------------------------------------------------------------------------------------
+// write = 0: only count the items (n_items); write = 1: emit descriptors at atomically claimed positions
+template <int W>
+__global__ void bmih_items_kernel(const BmihParams p, int write) {
+  const uint32_t n_buckets = p.m << p.sbits;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
+    const uint32_t cnt = p.boffs[b + 1] - p.boffs[b];
+    if (!cnt) continue;
+    const uint32_t t = b >> p.sbits, key = b & ((1u << p.sbits) - 1);
+    const uint32_t* rp = p.tables[t].row_ptr;
+    const uint32_t len = rp[key + 1] - rp[key];
+    const uint32_t nc = (len + p.cpi - 1) / p.cpi, nqc = (cnt + kBmihQT - 1) / kBmihQT;
+    const uint32_t base = atomicAdd(p.n_items, nc * nqc);
+    if (!write) atomicAdd(p.bucket_codes, (unsigned long long)len);
+    if (write)
+      for (uint32_t c = 0; c < nc; ++c)
+        for (uint32_t qc = 0; qc < nqc; ++qc) p.items[base + c * nqc + qc] = BmihItem{b, c, qc};
+  }
+}
+
+// ---- 3. verification ---------------------------------------------------------------------------------------
+// rare path: a code whose exact distance d passed tau of query qid
+template <int W>
+__device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
+                                         CodeRegs<W> c, const uint32_t* qw /* shared */) {
+  const BmihParams& p = *pp;
+  // first-discoverer test: table t found this code at substring distance exactly `radius`; it is emitted here
+  // only if no other table found it at a smaller distance, or at the same distance with a lower table id
+  uint32_t x[2 * W];
+#pragma unroll
+  for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qw[i];
+  for (uint32_t t2 = 0; t2 < p.m; ++t2) {
+    if (t2 == t) continue;
+    const uint32_t sd = __popc(substring<W>(x, t2, p.sbits));
+    if (sd < p.radius || (sd == p.radius && t2 < t)) return;
+  }
+  const uint64_t key = pack_key(d, p.tables[t].ids[j]);
+  if (key >= __ldcg(&p.gtaukey[qid])) return;
+  const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
+  if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
+  else atomicOr(&p.gflag[qid], 1u);
+  constexpr int HB = BmihCfg<W>::HB;
+  uint32_t* gh = p.ghist + (size_t)qid * HB;
+  atomicAdd(&gh[d], 1u);
+  const uint32_t tau = __ldcg(&p.gtau[qid]);
+  if (d < tau) {
+    uint32_t cum = 0;
+    const uint32_t lim = min(tau, (uint32_t)HB);
+    for (uint32_t b0 = 0; b0 < lim; b0 += 4) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(gh + b0));
+      const uint32_t e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cum += e[u];
+        if (cum >= p.k && b0 + u < lim) { atomicMin(&p.gtau[qid], b0 + u); return; }
+      }
+    }
+  }
+}
+
+template <int W, bool PREFILTER>
+__global__ void __launch_bounds__(kBmihThreads, 3) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
+  using Cfg = BmihCfg<W>;
+  constexpr int C = Cfg::C, QS = Cfg::QS;
+  __shared__ __align__(16) uint32_t s_qrec[kBmihQT * QS];
+  __shared__ uint32_t s_qid[kBmihQT];
+  __shared__ uint32_t s_item;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n_items = *p.n_items;
+  uint32_t next_it = 0;
+  if (tid == 0) next_it = atomicAdd(p.item_cursor, 1u);     // the claim for the next item is always one item ahead
+  for (;;) {
+    __syncthreads();                                   // previous item fully done with shared memory
+    if (tid == 0) { s_item = next_it; if (next_it < n_items) next_it = atomicAdd(p.item_cursor, 1u); }
+    __syncthreads();
+    const uint32_t it = s_item;
+    if (it >= n_items) break;
+    const BmihItem item = p.items[it];
+    const uint32_t t = item.bucket >> p.sbits, key = item.bucket & ((1u << p.sbits) - 1);
+    const TableDev& T = p.tables[t];
+    const uint32_t start = T.row_ptr[key], blen = T.row_ptr[key + 1] - start;
+    // the bucket's query list is cut into equal chunks of at most kBmihQT queries
+    const uint32_t qtot = p.boffs[item.bucket + 1] - p.boffs[item.bucket];
+    const uint32_t nqc = (qtot + kBmihQT - 1) / kBmihQT;
+    const uint32_t qlo = (uint32_t)(((uint64_t)qtot * item.q_chunk) / nqc), qhi = (uint32_t)(((uint64_t)qtot * (item.q_chunk + 1)) / nqc);
+    const uint32_t qbeg = p.boffs[item.bucket] + qlo;
+    const uint32_t qn = qhi - qlo;
+    // ---- stage the item's queries ------------------------------------------------------------------------
+    for (uint32_t e = tid; e < qn * QS; e += kBmihThreads) {
+      const uint32_t i = e / QS, w = e % QS;
+      const uint32_t qid = p.qlist[qbeg + i];
+      if (w == 0) s_qid[i] = qid;
+      s_qrec[e] = w < 2 * W ? p.queries[(size_t)qid * 2 * W + w] : (w == 2 * W ? __ldcg(&p.gtau[qid]) : 0u);
+    }
+    __syncthreads();
+    const uint32_t c0 = start + item.code_chunk * p.cpi;               // first code of this item (table order)
+    const uint32_t c1 = min(start + blen, c0 + p.cpi);                 // exclusive
+    const uint32_t a0 = W == 1 ? (c0 & ~1u) : c0;                      // 16-byte aligned start
+    const uint4* src = reinterpret_cast<const uint4*>(T.codes + (size_t)a0 * W);
+    for (uint32_t base = a0; base < c1; base += Cfg::STEP) {
+      CodeRegs<W> code[C];
+      const uint32_t u4_base = (base - a0) * W / 2;                    // in 16-byte units from src
+      const uint32_t u4_end = ((c1 - a0) * W + 1) / 2;
+#pragma unroll
+      for (int u = 0; u < kBmihU4; ++u) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if constexpr (W == 1) {
+          const uint32_t idx = u4_base + u * kBmihThreads + tid;
+          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          code[2 * u].w[0] = v.x; code[2 * u].w[1] = v.y; code[2 * u + 1].w[0] = v.z; code[2 * u + 1].w[1] = v.w;
+        } else if constexpr (W == 2) {
+          const uint32_t idx = u4_base + u * kBmihThreads + tid;
+          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          code[u].w[0] = v.x; code[u].w[1] = v.y; code[u].w[2] = v.z; code[u].w[3] = v.w;
+        } else {
+          const int cc = u / 2, h = u % 2;
+          const uint32_t idx = u4_base + 2 * (cc * kBmihThreads + tid) + h;
+          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          code[cc].w[4 * h + 0] = v.x; code[cc].w[4 * h + 1] = v.y; code[cc].w[4 * h + 2] = v.z; code[cc].w[4 * h + 3] = v.w;
+        }
+      }
+      auto local_of = [&](int c) -> uint32_t {
+        if constexpr (W == 1) return 2 * ((c / 2) * kBmihThreads + tid) + (c & 1);
+        else return c * kBmihThreads + tid;
+      };
+#pragma unroll 1
+      for (uint32_t q = 0; q < qn; ++q) {
+        uint32_t qw[2 * W];
+        const uint4* qv = reinterpret_cast<const uint4*>(s_qrec + q * QS);
+        uint32_t tau;
+        if constexpr (W == 1) {
+          const uint4 r = qv[0];
+          qw[0] = r.x; qw[1] = r.y; tau = r.z;
+        } else {
+#pragma unroll
+          for (int j = 0; j < W / 2; ++j) {
+            const uint4 r = qv[j];
+            qw[4 * j] = r.x; qw[4 * j + 1] = r.y; qw[4 * j + 2] = r.z; qw[4 * j + 3] = r.w;
+          }
+          tau = s_qrec[q * QS + 2 * W];
+        }
+        uint32_t mm[C];
+        uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          mm[c] = PREFILTER ? hamming_lower_bound<W>(code[c].w, qw) : hamming_exact<W>(code[c].w, qw);
+          mn = min(mn, mm[c]);
+        }
+        if (mn <= tau) {
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (mm[c] <= tau) {
+              const uint32_t d = PREFILTER ? hamming_exact<W>(code[c].w, qw) : mm[c];
+              const uint32_t j = base + local_of(c);
+              if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[q], t, d, j, code[c], s_qrec + q * QS);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- 4. settle: per query after a level ------------------------------------------------------------------
+// sort the candidate buffer, keep k, refresh thresholds / histogram, apply the stop rule for level `radius`
+template <int W>
+__global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, int count_probes,
+                                                          uint32_t* any_overflow) {
+  __shared__ uint64_t buf[kBmihCap];
+  __shared__ uint32_t cnt;
+  constexpr int HB = BmihCfg<W>::HB;
+  const uint32_t tid = threadIdx.x;
+  if (blockIdx.x >= n_list) return;
+  const uint32_t q = list ? list[blockIdx.x] : blockIdx.x;
+  const uint32_t raw = p.gcnt[q];
+  const uint32_t n = min(raw, (uint32_t)kBmihCap);
+  for (uint32_t i = tid; i < n; i += 256) buf[i] = p.gbuf[(size_t)q * kBmihCap + i];
+  if (tid == 0) cnt = n;
+  __syncthreads();
+  const uint64_t tk = topk_compact(buf, &cnt, kBmihCap, p.k, tid, 256, BlockSync());
+  const uint32_t kept = cnt;
+  for (uint32_t i = tid; i < kept; i += 256) p.gbuf[(size_t)q * kBmihCap + i] = buf[i];
+  uint32_t* gh = p.ghist + (size_t)q * HB;
+  for (uint32_t i = tid; i < HB; i += 256) gh[i] = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < kept; i += 256) atomicAdd(&gh[(uint32_t)(buf[i] >> 32)], 1u);
+  if (tid == 0) {
+    p.gcnt[q] = kept;
+    p.gtaukey[q] = tk;
+    if (tk != kEmptyKey) atomicMin(&p.gtau[q], (uint32_t)(tk >> 32));
+    const uint32_t r = p.radius;
+    bool stop = r >= p.sbits || (p.gflag[q] & 1u) != 0;                                  // overflowed queries are redone elsewhere
+    if (p.max_radius >= 0) stop = stop || r >= (uint32_t)p.max_radius;
+    else stop = stop || (kept == p.k && (uint32_t)(tk >> 32) + 1 <= p.m * (r + 1));      // search_worker.cc:204, strict and m-aware
+    p.gradius[q] = r;
+    if (count_probes) p.gprobes[q] += (unsigned long long)p.m * c_binom[p.sbits][r];   // n_sub_reads_ of this level
+    if (p.gflag[q] & 1u) *any_overflow = 1;
+    if (stop) atomicOr(&p.gflag[q], 2u);
+    else p.next_active[atomicAdd(p.n_next, 1u)] = q;
+  }
+}
+
+// per-query state at the start of a search; level-0 results (ascending keys, kEmptyKey padded) are imported
+__global__ void bmih_init_kernel(const BmihParams p, const uint64_t* keys0, const vc_query_stats* stats0, int hb) {
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  uint32_t c = 0;
+  for (uint32_t i = tid; i < p.k; i += blockDim.x) {
+    const uint64_t key = keys0[(size_t)q * p.k + i];
+    if (key != kEmptyKey) { p.gbuf[(size_t)q * kBmihCap + i] = key; ++c; }
+  }
+  __shared__ uint32_t total;
+  if (tid == 0) total = 0;
+  __syncthreads();
+  if (c) atomicAdd(&total, c);
+  __syncthreads();
+  if (tid == 0) {
+    p.gcnt[q] = total; p.gtau[q] = kInfDist; p.gtaukey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
+    p.gprobes[q] = stats0 ? stats0[q].probes : 0; p.gcands[q] = stats0 ? stats0[q].candidates : 0;
+  }
+  (void)hb;
+}
+
+__global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_query_stats* stats) {
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t kept = min(p.gcnt[q], p.k);
+  for (uint32_t i = tid; i < p.k; i += blockDim.x) out_keys[(size_t)q * p.k + i] = i < kept ? p.gbuf[(size_t)q * kBmihCap + i] : kEmptyKey;
+  if (stats && tid == 0) {
+    vc_query_stats st;
+    st.radius = p.gradius[q]; st.n_results = kept; st.probes = p.gprobes[q]; st.occupancy_tests = 0;
+    st.candidates = p.gcands[q]; st.unique = 0;
+    stats[q] = st;
+  }
+}
+
+// overflowed queries take their answer from the per-query kernel's output
+__global__ void bmih_patch_kernel(const uint32_t* gflag, uint32_t k, const uint64_t* redo_keys, const vc_query_stats* redo_stats,
+                                  uint64_t* out_keys, vc_query_stats* stats) {
+  const uint32_t q = blockIdx.x;
+  if (!(gflag[q] & 1u)) return;
+  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out_keys[(size_t)q * k + i] = redo_keys[(size_t)q * k + i];
+  if (stats && redo_stats && threadIdx.x == 0) stats[q] = redo_stats[q];
+}
+
+}  // namespace vc

@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
   for (;; ++radius) {                                                // search_worker.cc:170
     const uint32_t per_table = c_binom[sbits][radius];              // C(s, r) probes per table
     const uint64_t total = (uint64_t)per_table * m;
-    for (uint64_t g = (uint64_t)warp * 32; g < total; g += (uint64_t)kMihWarps * 32) {
+    // few probes (radius 0, 1): every warp visits every bucket and streams its own eighth of it; otherwise
+    // the warps take different groups of 32 probes
+    const bool split = total < (uint64_t)kMihWarps * 32 * 2;
+    for (uint64_t g = split ? 0 : (uint64_t)warp * 32; g < total; g += split ? 32 : (uint64_t)kMihWarps * 32) {
       // ---- one probe per lane ------------------------------------------------------------
       const uint64_t item = g + lane;
       uint32_t bt = 0, bstart = 0, blen = 0;
@@ -148,9 +151,11 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
         const uint32_t pidx = (uint32_t)(item % per_table);
         const uint32_t key = s_qkey[bt] ^ unrank_mask(sbits, radius, pidx);      // :260 curr ^ (1 << len)
         table_lookup(s_tab[bt], key, bstart, blen);                             // :246 proxy get
-        if (s_tab[bt].sparse) { ++my_occ; my_probes += blen ? 1 : 0; }           // :238-245
-        else ++my_probes;
-        my_cands += blen;
+        if (!split || warp == 0) {                                               // count each probe once
+          if (s_tab[bt].sparse) { ++my_occ; my_probes += blen ? 1 : 0; }         // :238-245
+          else ++my_probes;
+          my_cands += blen;
+        }
       }
       // ---- the warp streams the non-empty buckets one after the other -----------------------
       uint32_t todo = __ballot_sync(0xffffffffu, blen != 0);
@@ -169,7 +174,8 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
         constexpr int U = W == 4 ? 2 : 4;                   // groups per lane per iteration
         const uint32_t first = W == 1 ? (start & ~1u) : start;
         const uint32_t last = start + len;                  // exclusive
-        for (uint32_t j0 = first; j0 < last; j0 += 32 * CPL * U) {
+        const uint32_t jstep = 32 * CPL * U;
+        for (uint32_t j0 = first + (split ? warp * jstep : 0); j0 < last; j0 += split ? kMihWarps * jstep : jstep) {
           uint32_t cw[U][CPL][2 * W];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
