@@ -45,51 +45,51 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU sampled through NVML while the timed region runs."""
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period_s=0.2):
+        self.gpu, self.period = gpu_index, period_s
+        self.samples, self.reasons = [], set()
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_mhz = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for n, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+                self._stop.wait(self.period)
+        except Exception as ex:   # NVML missing: report it, never fake numbers
+            self.err = repr(ex)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self._thread = threading.Thread(target=self._loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 8:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=2)
+        if self.err or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable: %s" % self.err], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
 
 
 def make_queries(seed, nq, nbytes):
@@ -103,8 +103,8 @@ def reference_arm(args, n_total, world, rank):
         return
     from oracle import reference as ref, restatement as R
     cores = os.cpu_count() or 1
-    sample_n = int(os.environ.get("VC_BENCH_REF_N", 16_000_000))
-    nq = max(cores, 8)
+    sample_n = int(os.environ.get("VC_BENCH_REF_N", 64_000_000))
+    nq = max(cores, 8) * 4
     codes = R.synth_codes(DB_SEED, 0, sample_n, CODE_BITS // 8)
     mem = ref.RefMem(codes, 0)
     times = []
@@ -317,8 +317,8 @@ def main():
         try:
             from oracle import reference as ref, restatement as R
             cores = os.cpu_count() or 1
-            sample_n = int(os.environ.get("VC_BENCH_REF_N", 16_000_000))
-            nq_cpu = max(cores, 8)
+            sample_n = int(os.environ.get("VC_BENCH_REF_N", 64_000_000))
+            nq_cpu = max(cores, 8) * 8
             codes = R.synth_codes(DB_SEED, 0, sample_n, nbytes)
             mem = ref.RefMem(codes, 0)
             qh = make_queries(QUERY_SEED, nq_cpu, nbytes)

@@ -115,6 +115,7 @@ struct vc_index {
   int64_t mih_batched = -1;       // -1 auto, 0 per-query kernel only, 1 bucket-stationary batched path whenever legal
   int64_t mih_prefilter = -1;
   int64_t mih_cpi_steps = 0;
+  int64_t mih_wide = -1;
   int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
   int64_t profile = 0;
@@ -686,6 +687,17 @@ static int scan_inplace_small(vc_index* ix, uint32_t* d, uint64_t n, uint32_t* s
 }
 
 // Bucket-stationary batched MIH (bmih.cuh).  Exact or fixed-radius search over dense tables.
+template <int W, bool PF, int U4>
+static int launch_bmih_verify(const BmihParams& p, int num_sms, cudaStream_t st, int* grid_io) {
+  if (*grid_io == 0) {
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, PF, U4>, kBmihThreads, 0));
+    *grid_io = std::max(1, occ) * num_sms;
+  }
+  bmih_verify_kernel<W, PF, U4><<<*grid_io, kBmihThreads, 0, st>>>(p);
+  return VC_OK;
+}
+
 template <int W>
 static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int max_radius,
                        uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
@@ -714,6 +726,8 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     const uint64_t steps = std::min<uint64_t>(8, std::max<uint64_t>(2, (avg + Cfg::STEP - 1) / Cfg::STEP));
     p.cpi = ix->mih_cpi_steps > 0 ? (uint32_t)ix->mih_cpi_steps * Cfg::STEP : (uint32_t)steps * Cfg::STEP;
   }
+  // long buckets: 16 codes per thread per step (less loop overhead per pair); short ones: 8
+  const bool wide = ix->mih_wide > 0;   // measured slower than the 8-codes-per-thread variant at 3 CTAs/SM; kept as a knob
   p.bcount = (uint32_t*)ix->b_buckets.p; p.boffs = p.bcount + n_buckets;
   uint32_t* scan_sums = p.boffs + n_buckets + 1 + 3;
   p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
@@ -740,10 +754,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   uint32_t* cur = actA;
   uint32_t* nxt = actB;
   const bool pf = ix->mih_prefilter < 0 ? (W <= 2) : ix->mih_prefilter != 0;
-  int occ = 1;
-  if (pf) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, true>, kBmihThreads, 0));
-  else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, false>, kBmihThreads, 0));
-  const int verify_grid = std::max(1, occ) * ix->num_sms;
+  int verify_grid = 0;
   int levels = 0;
   int64_t items_total = 0;
   bool first_verify = true;
@@ -775,8 +786,9 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       if (!ix->lev[2 * levels]) { CU(cudaEventCreate(&ix->lev[2 * levels])); CU(cudaEventCreate(&ix->lev[2 * levels + 1])); }
       cudaEventRecord(ix->lev[2 * levels], st);
     }
-    if (pf) bmih_verify_kernel<W, true><<<verify_grid, kBmihThreads, 0, st>>>(p);
-    else bmih_verify_kernel<W, false><<<verify_grid, kBmihThreads, 0, st>>>(p);
+    if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
+    else rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &verify_grid);
+    if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
     first_verify = false;
     bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, 1, ctr + 3);
@@ -899,6 +911,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
   else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
+  else if (!strcmp(name, "mih.wide")) ix->mih_wide = value;
   else if (!strcmp(name, "profile")) {
     DeviceGuard g(ix->device);
     if (value && !ix->ev0) { CU(cudaEventCreate(&ix->ev0)); CU(cudaEventCreate(&ix->ev1)); }

@@ -29,10 +29,10 @@ namespace vc {
 constexpr int kBmihThreads = 256;
 constexpr int kBmihQT = 32;          // queries per work item
 constexpr int kBmihCap = 4096;       // candidate-buffer entries per query
-constexpr int kBmihU4 = 4;           // 128-bit loads per thread per step
+constexpr int kBmihU4 = 4;           // 128-bit loads per thread per step (short-bucket variant)
 
-template <int W> struct BmihCfg {
-  static constexpr int C = 2 * kBmihU4 / W;                 // codes per thread per step (8 / 4 / 2)
+template <int W, int U4 = kBmihU4> struct BmihCfg {
+  static constexpr int C = 2 * U4 / W;                      // codes per thread per step (U4 = 4: 8 / 4 / 2)
   static constexpr int STEP = kBmihThreads * C;             // codes per CTA step
   static constexpr int QS = (2 * W + 1 + 3) / 4 * 4;        // u32 per staged query: words, tau, pad
   static constexpr int HB = 64 * W + 32;
@@ -157,9 +157,9 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
   }
 }
 
-template <int W, bool PREFILTER>
-__global__ void __launch_bounds__(kBmihThreads, 3) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
-  using Cfg = BmihCfg<W>;
+template <int W, bool PREFILTER, int U4>
+__global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
+  using Cfg = BmihCfg<W, U4>;
   constexpr int C = Cfg::C, QS = Cfg::QS;
   __shared__ __align__(16) uint32_t s_qrec[kBmihQT * QS];
   __shared__ uint32_t s_qid[kBmihQT];
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kBmihThreads, 3) bmih_verify_kernel(const __gr
       const uint32_t u4_base = (base - a0) * W / 2;                    // in 16-byte units from src
       const uint32_t u4_end = ((c1 - a0) * W + 1) / 2;
 #pragma unroll
-      for (int u = 0; u < kBmihU4; ++u) {
+      for (int u = 0; u < U4; ++u) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if constexpr (W == 1) {
           const uint32_t idx = u4_base + u * kBmihThreads + tid;
@@ -222,22 +222,13 @@ __global__ void __launch_bounds__(kBmihThreads, 3) bmih_verify_kernel(const __gr
         if constexpr (W == 1) return 2 * ((c / 2) * kBmihThreads + tid) + (c & 1);
         else return c * kBmihThreads + tid;
       };
+      QRec<W> nxt = load_qrec<W, QS>(s_qrec, 0);
 #pragma unroll 1
       for (uint32_t q = 0; q < qn; ++q) {
-        uint32_t qw[2 * W];
-        const uint4* qv = reinterpret_cast<const uint4*>(s_qrec + q * QS);
-        uint32_t tau;
-        if constexpr (W == 1) {
-          const uint4 r = qv[0];
-          qw[0] = r.x; qw[1] = r.y; tau = r.z;
-        } else {
-#pragma unroll
-          for (int j = 0; j < W / 2; ++j) {
-            const uint4 r = qv[j];
-            qw[4 * j] = r.x; qw[4 * j + 1] = r.y; qw[4 * j + 2] = r.z; qw[4 * j + 3] = r.w;
-          }
-          tau = s_qrec[q * QS + 2 * W];
-        }
+        const QRec<W> cur = nxt;
+        if (q + 1 < qn) nxt = load_qrec<W, QS>(s_qrec, q + 1);      // next record's LDS overlaps this record's math
+        const uint32_t* qw = cur.qw;
+        const uint32_t tau = cur.tau;
         uint32_t mm[C];
         uint32_t mn = 0xFFFFFFFFu;
 #pragma unroll

@@ -101,6 +101,27 @@ __device__ __forceinline__ uint32_t hamming_lower_bound(const uint32_t* __restri
   return d;
 }
 
+// One staged query record in shared memory: 2W query words, then the distance threshold (stride QS u32,
+// 16-byte aligned).  Loaded with 128-bit LDS; the loops prefetch record q+1 while testing record q.
+template <int W> struct QRec { uint32_t qw[2 * W]; uint32_t tau; };
+template <int W, int QS>
+__device__ __forceinline__ QRec<W> load_qrec(const uint32_t* base, uint32_t q) {
+  QRec<W> r;
+  const uint4* qv = reinterpret_cast<const uint4*>(base + q * QS);
+  if constexpr (W == 1) {
+    const uint4 v = qv[0];
+    r.qw[0] = v.x; r.qw[1] = v.y; r.tau = v.z;
+  } else {
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) {
+      const uint4 v = qv[j];
+      r.qw[4 * j] = v.x; r.qw[4 * j + 1] = v.y; r.qw[4 * j + 2] = v.z; r.qw[4 * j + 3] = v.w;
+    }
+    r.tau = base[q * QS + 2 * W];
+  }
+  return r;
+}
+
 // splitmix64-based synthetic code words (must match oracle/verticut_oracle.c: vo_synth_word)
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -248,22 +248,13 @@ __global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanPa
     uint32_t appended = 0;
     if (!careful) {
       // ---- fast path: every query of the tile against the C codes in registers ---------------------
+      QRec<W> nxt = load_qrec<W, QS>(s.qrec, 0);
 #pragma unroll 1
       for (uint32_t q = 0; q < nq_here; ++q) {
-        uint32_t qw[2 * W];
-        const uint4* qv = reinterpret_cast<const uint4*>(s.qrec + q * QS);
-        uint32_t tau;
-        if constexpr (W == 1) {
-          const uint4 r = qv[0];
-          qw[0] = r.x; qw[1] = r.y; tau = r.z;
-        } else {
-#pragma unroll
-          for (int j = 0; j < W / 2; ++j) {
-            const uint4 r = qv[j];
-            qw[4 * j] = r.x; qw[4 * j + 1] = r.y; qw[4 * j + 2] = r.z; qw[4 * j + 3] = r.w;
-          }
-          tau = s.qrec[q * QS + 2 * W];
-        }
+        const QRec<W> cur = nxt;
+        if (q + 1 < nq_here) nxt = load_qrec<W, QS>(s.qrec, q + 1);      // next record's LDS overlaps this record's math
+        const uint32_t* qw = cur.qw;
+        const uint32_t tau = cur.tau;
         uint32_t m[C];
         uint32_t mn = 0xFFFFFFFFu;
 #pragma unroll
