@@ -1,2 +1,4 @@
+timeout 900 python -m pytest tests/test_gpu_bmih.py -m gpu -x -q 2>&1 | tail -3
 python tools/scan_probe.py mih 1000000000 4096
 python tools/scan_probe.py mih 125000000 4096
+python tools/scan_probe.py mih 100000000 1024

@@ -38,7 +38,8 @@ template <int W, int U4 = kBmihU4> struct BmihCfg {
   static constexpr int HB = 64 * W + 32;
 };
 
-struct BmihItem { uint32_t bucket, code_chunk, q_chunk; };
+// one work item: codes [c0, c1) of table t (bucket order) against queries qlist[qbeg, qbeg + qn)
+struct BmihItem { uint32_t t, c0, c1, qbeg, qn; };
 
 struct BmihParams {
   const uint32_t* queries;      // [nq][2W]
@@ -111,9 +112,18 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
     const uint32_t nc = (len + p.cpi - 1) / p.cpi, nqc = (cnt + kBmihQT - 1) / kBmihQT;
     const uint32_t base = atomicAdd(p.n_items, nc * nqc);
     if (!write) atomicAdd(p.bucket_codes, (unsigned long long)len);
-    if (write)
+    if (write) {
+      const uint32_t start = rp[key];
       for (uint32_t c = 0; c < nc; ++c)
-        for (uint32_t qc = 0; qc < nqc; ++qc) p.items[base + c * nqc + qc] = BmihItem{b, c, qc};
+        for (uint32_t qc = 0; qc < nqc; ++qc) {
+          // the bucket's query list is cut into equal chunks of at most kBmihQT queries
+          const uint32_t qlo = (uint32_t)(((uint64_t)cnt * qc) / nqc), qhi = (uint32_t)(((uint64_t)cnt * (qc + 1)) / nqc);
+          BmihItem it;
+          it.t = t; it.c0 = start + c * p.cpi; it.c1 = min(start + len, it.c0 + p.cpi);
+          it.qbeg = p.boffs[b] + qlo; it.qn = qhi - qlo;
+          p.items[base + c * nqc + qc] = it;
+        }
+    }
   }
 }
 
@@ -157,71 +167,81 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
   }
 }
 
+// Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
+// item's queries in its slice of shared memory and streams the item's codes 32 lanes x C codes at a time.
 template <int W, bool PREFILTER, int U4>
 __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
   using Cfg = BmihCfg<W, U4>;
   constexpr int C = Cfg::C, QS = Cfg::QS;
-  __shared__ __align__(16) uint32_t s_qrec[kBmihQT * QS];
-  __shared__ uint32_t s_qid[kBmihQT];
-  __shared__ uint32_t s_item;
-  const uint32_t tid = threadIdx.x;
+  constexpr int NW = kBmihThreads / 32;
+  constexpr uint32_t WSTEP = 32 * C;                       // codes per warp step
+  __shared__ __align__(16) uint32_t s_qrec_all[NW][kBmihQT * QS];
+  __shared__ uint32_t s_qid_all[NW][kBmihQT];
+  __shared__ const uint64_t* s_codes[kMaxTables];          // table payload pointers, fetched once
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < p.m) s_codes[tid] = p.tables[tid].codes;
+  __syncthreads();
+  uint32_t* s_qrec = s_qrec_all[warp];
+  uint32_t* s_qid = s_qid_all[warp];
   const uint32_t n_items = *p.n_items;
-  uint32_t next_it = 0;
-  if (tid == 0) next_it = atomicAdd(p.item_cursor, 1u);     // the claim for the next item is always one item ahead
+  // lane 0 runs one item ahead: the claim (atomic) and the descriptor of the next item are fetched while the
+  // warp works on the current one
+  uint32_t next_it = n_items;
+  BmihItem nd = BmihItem{0, 0, 0, 0, 0};
+  if (lane == 0) {
+    next_it = atomicAdd(p.item_cursor, 1u);
+    if (next_it < n_items) nd = p.items[next_it];
+  }
   for (;;) {
-    __syncthreads();                                   // previous item fully done with shared memory
-    if (tid == 0) { s_item = next_it; if (next_it < n_items) next_it = atomicAdd(p.item_cursor, 1u); }
-    __syncthreads();
-    const uint32_t it = s_item;
+    const uint32_t it = __shfl_sync(0xffffffffu, next_it, 0);
     if (it >= n_items) break;
-    const BmihItem item = p.items[it];
-    const uint32_t t = item.bucket >> p.sbits, key = item.bucket & ((1u << p.sbits) - 1);
-    const TableDev& T = p.tables[t];
-    const uint32_t start = T.row_ptr[key], blen = T.row_ptr[key + 1] - start;
-    // the bucket's query list is cut into equal chunks of at most kBmihQT queries
-    const uint32_t qtot = p.boffs[item.bucket + 1] - p.boffs[item.bucket];
-    const uint32_t nqc = (qtot + kBmihQT - 1) / kBmihQT;
-    const uint32_t qlo = (uint32_t)(((uint64_t)qtot * item.q_chunk) / nqc), qhi = (uint32_t)(((uint64_t)qtot * (item.q_chunk + 1)) / nqc);
-    const uint32_t qbeg = p.boffs[item.bucket] + qlo;
-    const uint32_t qn = qhi - qlo;
-    // ---- stage the item's queries ------------------------------------------------------------------------
-    for (uint32_t e = tid; e < qn * QS; e += kBmihThreads) {
+    const uint32_t t = __shfl_sync(0xffffffffu, nd.t, 0);
+    const uint32_t c0 = __shfl_sync(0xffffffffu, nd.c0, 0), c1 = __shfl_sync(0xffffffffu, nd.c1, 0);
+    const uint32_t qbeg = __shfl_sync(0xffffffffu, nd.qbeg, 0), qn = __shfl_sync(0xffffffffu, nd.qn, 0);
+    if (lane == 0) {
+      next_it = atomicAdd(p.item_cursor, 1u);
+      if (next_it < n_items) nd = p.items[next_it];
+    }
+    const uint32_t a0 = W == 1 ? (c0 & ~1u) : c0;                      // 16-byte aligned start
+    const uint4* src = reinterpret_cast<const uint4*>(s_codes[t] + (size_t)a0 * W);
+    const uint32_t u4_end = ((c1 - a0) * W + 1) / 2;                   // 16-byte units of the item
+    CodeRegs<W> code[C];
+    auto load_step = [&](uint32_t base) {
+      const uint32_t u4_base = (base - a0) * W / 2;
+#pragma unroll
+      for (int u = 0; u < U4; ++u) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if constexpr (W == 1) {
+          const uint32_t idx = u4_base + u * 32 + lane;
+          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          code[2 * u].w[0] = v.x; code[2 * u].w[1] = v.y; code[2 * u + 1].w[0] = v.z; code[2 * u + 1].w[1] = v.w;
+        } else if constexpr (W == 2) {
+          const uint32_t idx = u4_base + u * 32 + lane;
+          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          code[u].w[0] = v.x; code[u].w[1] = v.y; code[u].w[2] = v.z; code[u].w[3] = v.w;
+        } else {
+          const int cc = u / 2, h = u % 2;
+          const uint32_t idx = u4_base + 2 * (cc * 32 + lane) + h;
+          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          code[cc].w[4 * h + 0] = v.x; code[cc].w[4 * h + 1] = v.y; code[cc].w[4 * h + 2] = v.z; code[cc].w[4 * h + 3] = v.w;
+        }
+      }
+    };
+    auto local_of = [&](int c) -> uint32_t {
+      if constexpr (W == 1) return 2 * ((c / 2) * 32 + lane) + (c & 1);
+      else return c * 32 + lane;
+    };
+    load_step(a0);                                     // the first codes travel while the queries are staged
+    __syncwarp();                                      // previous item's readers are done with the warp's slice
+    for (uint32_t e = lane; e < qn * QS; e += 32) {
       const uint32_t i = e / QS, w = e % QS;
       const uint32_t qid = p.qlist[qbeg + i];
       if (w == 0) s_qid[i] = qid;
       s_qrec[e] = w < 2 * W ? p.queries[(size_t)qid * 2 * W + w] : (w == 2 * W ? __ldcg(&p.gtau[qid]) : 0u);
     }
-    __syncthreads();
-    const uint32_t c0 = start + item.code_chunk * p.cpi;               // first code of this item (table order)
-    const uint32_t c1 = min(start + blen, c0 + p.cpi);                 // exclusive
-    const uint32_t a0 = W == 1 ? (c0 & ~1u) : c0;                      // 16-byte aligned start
-    const uint4* src = reinterpret_cast<const uint4*>(T.codes + (size_t)a0 * W);
-    for (uint32_t base = a0; base < c1; base += Cfg::STEP) {
-      CodeRegs<W> code[C];
-      const uint32_t u4_base = (base - a0) * W / 2;                    // in 16-byte units from src
-      const uint32_t u4_end = ((c1 - a0) * W + 1) / 2;
-#pragma unroll
-      for (int u = 0; u < U4; ++u) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if constexpr (W == 1) {
-          const uint32_t idx = u4_base + u * kBmihThreads + tid;
-          if (idx < u4_end) v = ld_stream_u4(src + idx);
-          code[2 * u].w[0] = v.x; code[2 * u].w[1] = v.y; code[2 * u + 1].w[0] = v.z; code[2 * u + 1].w[1] = v.w;
-        } else if constexpr (W == 2) {
-          const uint32_t idx = u4_base + u * kBmihThreads + tid;
-          if (idx < u4_end) v = ld_stream_u4(src + idx);
-          code[u].w[0] = v.x; code[u].w[1] = v.y; code[u].w[2] = v.z; code[u].w[3] = v.w;
-        } else {
-          const int cc = u / 2, h = u % 2;
-          const uint32_t idx = u4_base + 2 * (cc * kBmihThreads + tid) + h;
-          if (idx < u4_end) v = ld_stream_u4(src + idx);
-          code[cc].w[4 * h + 0] = v.x; code[cc].w[4 * h + 1] = v.y; code[cc].w[4 * h + 2] = v.z; code[cc].w[4 * h + 3] = v.w;
-        }
-      }
-      auto local_of = [&](int c) -> uint32_t {
-        if constexpr (W == 1) return 2 * ((c / 2) * kBmihThreads + tid) + (c & 1);
-        else return c * kBmihThreads + tid;
-      };
+    __syncwarp();
+    for (uint32_t base = a0; base < c1; base += WSTEP) {
+      if (base != a0) load_step(base);
       QRec<W> nxt = load_qrec<W, QS>(s_qrec, 0);
 #pragma unroll 1
       for (uint32_t q = 0; q < qn; ++q) {
