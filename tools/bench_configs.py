@@ -1,0 +1,70 @@
+"""One-GPU measurements of the BASELINE.json configs that are not the bench.py headline (C1, C2, C3-per-GPU-shard, C5),
+each checked for self-consistency (MIH == linear scan on the same index) on a few queries.
+    python tools/bench_configs.py > profiles/configs_r01.json"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from verticut_b200 import capi  # noqa: E402
+
+PEAK = 6554.6
+
+
+def timed(fn, reps=3):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def run(name, n, bits, m, k, nq, max_radius=-1, check=8, scan_batches=(1, 256)):
+    nbytes = bits // 8
+    out = {"config": name, "n_codes": n, "code_bits": bits, "tables": m, "k": k, "batch": nq}
+    ix = capi.Index(bits, m)
+    t0 = time.perf_counter()
+    ix.add_synthetic(n, 12345)
+    ix.build()
+    out["build_s"] = time.perf_counter() - t0
+    out["index_GB"] = ix.info()["device_bytes"] / 1e9
+    ix.set_param("profile", 1)
+    q = np.random.default_rng(67890).integers(0, 256, size=(nq, nbytes), dtype=np.uint8)
+    if m:
+        ids, dists, counts, st = ix.search_mih(q, k, max_radius=max_radius)
+        dt = timed(lambda: ix.search_mih(q, k, max_radius=max_radius, with_stats=False))
+        kern = ix.get_param("last_kernel_ns") * 1e-9
+        out["mih"] = {"queries_per_s_e2e": nq / dt, "kernel_ms": kern * 1e3, "batched": bool(ix.get_param("mih.last_batched")),
+                      "mean_radius": float(st["radius"].mean()), "probes_per_query": float(st["probes"].mean()),
+                      "candidates_per_query": float(st["candidates"].mean()),
+                      "pairs_per_s": float(st["candidates"].sum()) / kern,
+                      "per_query_formula_GBps": float(st["probes"].sum() * 8 + st["candidates"].sum() * nbytes) / kern / 1e9}
+        if max_radius < 0 and check:
+            lid, ld, lc = ix.search_linear(q[:check], k)
+            out["mih"]["equals_linear_scan"] = bool(np.array_equal(lid, ids[:check]) and np.array_equal(ld, dists[:check]))
+    out["scan"] = {}
+    for B in scan_batches:
+        qq = q[:B] if B <= nq else np.random.default_rng(1).integers(0, 256, size=(B, nbytes), dtype=np.uint8)
+        dt = timed(lambda: ix.search_linear(qq, k), reps=2)
+        kern = ix.get_param("last_kernel_ns") * 1e-9
+        out["scan"]["B=%d" % B] = {"queries_per_s_e2e": len(qq) / dt, "kernel_ms": kern * 1e3,
+                                  "hbm_GBps": n * nbytes / kern / 1e9, "frac_of_measured_peak": n * nbytes / kern / 1e9 / PEAK,
+                                  "pairs_per_s": len(qq) * n / kern}
+    ix.close()
+    return out
+
+
+if __name__ == "__main__":
+    res = []
+    res.append(run("C1 linear 1M x 64-bit, 1k queries, k=10 (GPU; MIH m=4 beside it)", 1_000_000, 64, 4, 10, 1000, scan_batches=(1000,)))
+    res.append(run("C2 MIH 64-bit m=4, 100M codes, k=100", 100_000_000, 64, 4, 100, 4096))
+    res.append(run("C3 shard: MIH 128-bit m=8, 125M codes (1/8 of 1B), k=100", 125_000_000, 128, 8, 100, 1024))
+    for r in (0, 1, 2, 3):
+        res.append(run("C5 (reduced N to fit one GPU) MIH 256-bit m=16, 60M codes, k=1000, fixed radius %d" % r, 60_000_000, 256, 16,
+                       1000, 256, max_radius=r, scan_batches=(1,) if r == 0 else ()))
+    res.append(run("C5 sparse: MIH 256-bit m=8 (s=32 bitmap tables), 60M codes, k=1000, fixed radius 2", 60_000_000, 256, 8, 1000, 64,
+                   max_radius=2, scan_batches=()))
+    print(json.dumps(res, indent=1))

@@ -248,11 +248,9 @@ __global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanPa
     uint32_t appended = 0;
     if (!careful) {
       // ---- fast path: every query of the tile against the C codes in registers ---------------------
-      QRec<W> nxt = load_qrec<W, QS>(s.qrec, 0);
 #pragma unroll 1
       for (uint32_t q = 0; q < nq_here; ++q) {
-        const QRec<W> cur = nxt;
-        if (q + 1 < nq_here) nxt = load_qrec<W, QS>(s.qrec, q + 1);      // next record's LDS overlaps this record's math
+        const QRec<W> cur = load_qrec<W, QS>(s.qrec, q);
         const uint32_t* qw = cur.qw;
         const uint32_t tau = cur.tau;
         uint32_t m[C];
