@@ -116,6 +116,7 @@ struct vc_index {
   int64_t mih_prefilter = -1;
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
+  int64_t mih_min_bucket = 64;    // batched path when the average bucket holds at least this many codes
   int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
   int64_t profile = 0;
@@ -710,11 +711,9 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
                o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
                o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
-               o_ctr = take(64);
+               o_ctr = take(128);
   if ((rc = ix->b_state.ensure(off))) return rc;
   if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024))) return rc;
-  if ((rc = ix->b_keys0.ensure((size_t)nq * k * 8))) return rc;
-  if ((rc = ix->b_stats0.ensure((size_t)nq * sizeof(vc_query_stats)))) return rc;
   unsigned char* sb = (unsigned char*)ix->b_state.p;
   uint32_t* ctr = (uint32_t*)(sb + o_ctr);            // [0] n_items  [1] item_cursor  [2] n_next  [3] any_overflow
   BmihParams p;
@@ -738,19 +737,14 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   uint32_t* actA = (uint32_t*)(sb + o_actA);
   uint32_t* actB = (uint32_t*)(sb + o_actB);
 
-  // ---- level 0: the query's own buckets, by the per-query kernel (bounded memory while tau is unknown) ----
-  uint64_t* keys0 = (uint64_t*)ix->b_keys0.p;
-  vc_query_stats* stats0 = (vc_query_stats*)ix->b_stats0.p;
-  if ((rc = mih_per_query(ix, d_queries, nq, k, 0, 0, keys0, stats0, st))) return rc;
-  CU(cudaMemsetAsync(ctr, 0, 64, st));
-  bmih_init_kernel<<<nq, 128, 0, st>>>(p, keys0, stats0, Cfg::HB);
-  p.next_active = actA;
-  bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, nullptr, nq, 0, ctr + 3);
+  // ---- start: all queries active, thresholds bootstrapped from a sample of each query's own buckets -------
+  CU(cudaMemsetAsync(ctr, 0, 128, st));
+  CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));      // histograms count this search's candidates only
+  bmih_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p, actA);
+  bmih_bootstrap_kernel<W><<<(nq + 7) / 8, 256, 0, st>>>(p);
   ix->launches += 2;
-  uint32_t h_ctr[4];
-  CU(cudaMemcpyAsync(h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  uint32_t n_active = h_ctr[2];
+  uint32_t h_ctr[4] = {0, 0, 0, 0};
+  uint32_t n_active = nq;
   uint32_t* cur = actA;
   uint32_t* nxt = actB;
   const bool pf = ix->mih_prefilter < 0 ? (W <= 2) : ix->mih_prefilter != 0;
@@ -758,7 +752,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   int levels = 0;
   int64_t items_total = 0;
   bool first_verify = true;
-  for (uint32_t r = 1; n_active > 0 && r <= sbits; ++r) {
+  for (uint32_t r = 0; n_active > 0 && r <= sbits; ++r) {
     p.radius = r; p.active = cur; p.n_active = n_active; p.next_active = nxt;
     const uint64_t total_probes = (uint64_t)n_active * m * host_binom(sbits, r);
     if ((rc = ix->b_qlist.ensure(std::max<uint64_t>(total_probes, 1) * 4))) return rc;
@@ -836,7 +830,7 @@ int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t
   // Bucket-stationary batching pays when several queries share a bucket and buckets are long enough to
   // fill a CTA step; it needs dense tables and no distinct-candidate count (approximate mode).
   const bool legal = ix->sbits <= 16 && !(approximate != 0 && max_radius < 0) && k < (uint32_t)kBmihCap / 2;
-  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && nq >= 64 && (ix->n >> ix->sbits) >= 256);
+  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && (ix->n >> ix->sbits) >= (uint64_t)ix->mih_min_bucket);
   ix->last_mih_batched = 0;
   if (legal && want) {
     if (ix->W == 1) return mih_batched<1>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
@@ -912,6 +906,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
   else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
   else if (!strcmp(name, "mih.wide")) ix->mih_wide = value;
+  else if (!strcmp(name, "mih.min_bucket")) ix->mih_min_bucket = value;
   else if (!strcmp(name, "profile")) {
     DeviceGuard g(ix->device);
     if (value && !ix->ev0) { CU(cudaEventCreate(&ix->ev0)); CU(cudaEventCreate(&ix->ev1)); }

@@ -17,9 +17,9 @@
 //                          threshold tau[q] is the exact running k-th distance (global histogram + atomicMin);
 //   4. bmih_settle_kernel  per query: sort the buffer, keep the k best (the heap of :192-197), apply the
 //                          strict m-aware stop rule (:201-207) and build the next active list.
-// Level 0 (the query's own bucket in every table) is done by mih_search_kernel with max_radius = 0, which
-// also bounds memory when nothing is known about the distances yet.  A query whose candidate buffer
-// overflows (adversarial ties) is re-run by the per-query kernel, so the result is exact whatever the data.
+// Before level 0 a bootstrap kernel bounds every query's k-th distance from a sample of its own buckets, so
+// that the candidate buffers stay small from the first level on.  A query whose candidate buffer overflows
+// all the same (adversarial ties) is re-run by the per-query kernel, so the result is exact whatever the data.
 #pragma once
 #include "mih.cuh"
 #include "scan.cuh"
@@ -310,24 +310,64 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   }
 }
 
-// per-query state at the start of a search; level-0 results (ascending keys, kEmptyKey padded) are imported
-__global__ void bmih_init_kernel(const BmihParams p, const uint64_t* keys0, const vc_query_stats* stats0, int hb) {
-  const uint32_t q = blockIdx.x, tid = threadIdx.x;
-  uint32_t c = 0;
-  for (uint32_t i = tid; i < p.k; i += blockDim.x) {
-    const uint64_t key = keys0[(size_t)q * p.k + i];
-    if (key != kEmptyKey) { p.gbuf[(size_t)q * kBmihCap + i] = key; ++c; }
+// per-query state at the start of a search
+__global__ void bmih_init_kernel(const BmihParams p, uint32_t* active0) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.nq) return;
+  p.gcnt[q] = 0; p.gtau[q] = kInfDist; p.gtaukey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
+  p.gprobes[q] = 0; p.gcands[q] = 0;
+  active0[q] = q;
+}
+
+// Bootstrap of the distance thresholds: before level 0 nothing is known about the k-th distance, and with
+// tau = infinity every member of the query's own buckets (N / 2^s codes per table) would have to be buffered.
+// One warp per query looks at up to kBmihSample codes of those buckets (table 0 first), histograms their
+// distances (each code once: the first-discoverer rule at radius 0) and sets tau[q] to the k-th smallest -
+// a valid bound, since these are real database codes that level 0 will find again.
+constexpr uint32_t kBmihSample = 4096;     // at least; 16 * k when that is more
+template <int W>
+__global__ void __launch_bounds__(256) bmih_bootstrap_kernel(const BmihParams p) {
+  constexpr int HB = BmihCfg<W>::HB;
+  __shared__ uint32_t s_hist[8][HB];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t q = blockIdx.x * 8 + warp;
+  if (q >= p.nq) return;
+  uint32_t* h = s_hist[warp];
+  for (uint32_t i = lane; i < HB; i += 32) h[i] = 0;
+  __syncwarp();
+  uint32_t qw[2 * W];
+#pragma unroll
+  for (int i = 0; i < 2 * W; ++i) qw[i] = p.queries[(size_t)q * 2 * W + i];
+  uint32_t taken = 0;
+  const uint32_t sample = max(kBmihSample, 16u * p.k);
+  for (uint32_t t = 0; t < p.m && taken < sample; ++t) {
+    const uint32_t key = substring<W>(qw, t, p.sbits);
+    const uint32_t start = p.tables[t].row_ptr[key], len = p.tables[t].row_ptr[key + 1] - start;
+    const uint32_t take = min(len, sample - taken);
+    const uint64_t* codes = p.tables[t].codes;
+    for (uint32_t j = lane; j < take; j += 32) {
+      uint32_t x[2 * W];
+      uint32_t d = 0;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const uint64_t c = codes[(size_t)(start + j) * W + i];
+        x[2 * i] = (uint32_t)c ^ qw[2 * i]; x[2 * i + 1] = (uint32_t)(c >> 32) ^ qw[2 * i + 1];
+        d += __popc(x[2 * i]) + __popc(x[2 * i + 1]);
+      }
+      bool first = true;                          // already counted from a lower table whose substring also matches?
+      for (uint32_t t2 = 0; t2 < t; ++t2) first = first && substring<W>(x, t2, p.sbits) != 0;
+      if (first) atomicAdd(&h[d], 1u);
+    }
+    taken += take;
   }
-  __shared__ uint32_t total;
-  if (tid == 0) total = 0;
-  __syncthreads();
-  if (c) atomicAdd(&total, c);
-  __syncthreads();
-  if (tid == 0) {
-    p.gcnt[q] = total; p.gtau[q] = kInfDist; p.gtaukey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
-    p.gprobes[q] = stats0 ? stats0[q].probes : 0; p.gcands[q] = stats0 ? stats0[q].candidates : 0;
+  __syncwarp();
+  if (lane == 0) {
+    uint32_t cum = 0;
+    for (uint32_t d = 0; d <= 64 * W; ++d) {
+      cum += h[d];
+      if (cum >= p.k) { p.gtau[q] = d; break; }
+    }
   }
-  (void)hb;
 }
 
 __global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_query_stats* stats) {
