@@ -7,7 +7,7 @@ import numpy as np
 from . import ORACLE_SO, build
 
 ORDER_CANONICAL, ORDER_REFERENCE = 0, 1
-STOP_REF4, STOP_STRICT_M, STOP_REF_M = 0, 1, 2
+STOP_REF4, STOP_STRICT_M, STOP_REF_M, STOP_TABLE_STRICT = 0, 1, 2, 3
 APPROX_FACTOR = 20
 
 _lib = None

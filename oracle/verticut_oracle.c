@@ -40,6 +40,10 @@
 #define VO_STOP_REF4 0      /* full && top.dist <= (r+1)*4      search_worker.cc:201-205 */
 #define VO_STOP_STRICT_M 1  /* full && d_k <= m*(r+1) - 1        SURVEY.md finding 7 */
 #define VO_STOP_REF_M 2     /* full && top.dist <= (r+1)*m       finding 6 only */
+#define VO_STOP_TABLE_STRICT 3 /* checked after EVERY table t of radius r: full && d_k <= m*r + t.  Codes not yet found
+                                  then have substring distance >= r+1 in tables 0..t and >= r in the others, i.e. full
+                                  distance >= m*r + t + 1 > d_k: the canonical top-k is final.  Same answers as
+                                  VO_STOP_STRICT_M with fewer probes (canonical order only). */
 
 #define VO_APPROX_FACTOR 20 /* search_worker.h:14 APPROXIMATE_FACTOR */
 
@@ -318,7 +322,21 @@ uint32_t vo_mih_search(const vo_index* ix, const uint8_t* query, uint32_t k, int
     for (int t = 0; t < ix->m; ++t) { /* ranks = tables; gather_vectors concatenates in rank order (mpi_coordinator.cc:50-59) */
       e.table = (uint32_t)t;
       enumerate_entry(&e, search_index[t], 0, radius); /* :222-227 */
+      if (stop == VO_STOP_TABLE_STRICT && order == VO_ORDER_CANONICAL && !approximate && max_radius < 0) {
+        /* table-granular variant: digest this table's candidates now and test the stop rule */
+        for (size_t i = 0; i < e.ncand; ++i) {
+          uint32_t id = (uint32_t)e.cand[i];
+          uint64_t ord = id - ix->first_id;
+          if (seen[ord / 64] >> (ord % 64) & 1) continue;
+          seen[ord / 64] |= 1ull << (ord % 64);
+          st.unique++;
+          topk_offer(&tk, e.cand[i]);
+        }
+        e.ncand = 0;
+        if (tk.n == tk.k && tk.k > 0 && (uint32_t)(tk.a[tk.n - 1] >> 32) <= (uint32_t)(ix->m * radius + t)) { is_stop = 1; break; }
+      }
     }
+    if (is_stop) { radius += 1; break; }
     for (size_t i = 0; i < e.ncand; ++i) { /* master loop :179-199 */
       uint32_t id = (uint32_t)e.cand[i], dist = (uint32_t)(e.cand[i] >> 32);
       uint64_t ord = id - ix->first_id;
@@ -349,7 +367,7 @@ uint32_t vo_mih_search(const vo_index* ix, const uint8_t* query, uint32_t k, int
       if (tk.n == tk.k && tk.k > 0) {
         uint32_t dk = (uint32_t)(tk.a[tk.n - 1] >> 32);
         uint32_t mult = stop == VO_STOP_REF4 ? 4u : (uint32_t)ix->m;
-        if (stop == VO_STOP_STRICT_M ? (dk + 1 <= (uint32_t)radius * mult) : (dk <= (uint32_t)radius * mult)) is_stop = 1;
+        if (stop == VO_STOP_STRICT_M || stop == VO_STOP_TABLE_STRICT ? (dk + 1 <= (uint32_t)radius * mult) : (dk <= (uint32_t)radius * mult)) is_stop = 1;
       }
     }
   }

@@ -52,8 +52,35 @@ def test_batched_large_batch_matches_per_query_kernel(oracle):
     assert ix.get_param("mih.last_batched") == 1
     for x, y in zip(a[:3], b[:3]):
         np.testing.assert_array_equal(x, y)
-    for f in ("radius", "n_results", "probes", "candidates"):
+    for f in ("radius", "n_results"):
         np.testing.assert_array_equal(a[3][f], b[3][f])
+    for steps in (0, 1):                      # same stop rhythm -> same probe / candidate counts on both paths
+        ix.set_param("mih.table_steps", steps)
+        ix.set_param("mih.batched", 0)
+        a2 = ix.search_mih(queries[:64], k)
+        ix.set_param("mih.batched", 1)
+        b2 = ix.search_mih(queries[:64], k)
+        for f in ("radius", "n_results", "probes", "candidates"):
+            np.testing.assert_array_equal(a2[3][f], b2[3][f])
+        np.testing.assert_array_equal(a2[0], b2[0])
+    ix.set_param("mih.table_steps", -1)
     lid, ld, lc = ix.search_linear(queries[:16], k)
     np.testing.assert_array_equal(b[0][:16], lid)
+    ix.close()
+
+
+def test_batched_state_is_clean_between_calls(oracle):
+    # the per-query device state is reused across calls and batch sizes; answers must not depend on history
+    n, k = 300_000, 50
+    ix = capi.Index(64, 4)
+    ix.add_synthetic(n, 12345)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    for nq, seed in ((200, 1), (7, 2), (200, 3), (1, 4)):
+        q = oracle.synth_codes(seed, 0, nq, 8)
+        ids, dists, counts, _ = ix.search_mih(q, k)
+        oid, od, oc = oracle.linear_search(codes, q[:5], k)
+        np.testing.assert_array_equal(ids[:5], oid)
+        np.testing.assert_array_equal(dists[:5], od)
     ix.close()

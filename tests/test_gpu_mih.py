@@ -73,26 +73,31 @@ def test_occupancy_bitmap_matches_oracle(oracle, bits, m):
 def _check_exact(oracle, n, bits, m, nq, k, first_id=0):
     codes, ix = _mk(oracle, n, bits, m, first_id=first_id)
     queries = oracle.synth_codes(67890, 0, nq, bits // 8)
-    ids, dists, counts, stats = ix.search_mih(queries, k)
     lid, ld, lc = oracle.linear_search(codes, queries, k, first_id=first_id)
-    np.testing.assert_array_equal(counts, lc)
-    np.testing.assert_array_equal(dists, ld)
-    np.testing.assert_array_equal(ids, lid)
-    gid, gd, gc = ix.search_linear(queries, k)
-    np.testing.assert_array_equal(gid, ids)
-    np.testing.assert_array_equal(gd, dists)
-    # statistics against the canonical oracle MIH (strict m-aware stop rule)
     oix = oracle.Index(codes, m, first_id=first_id)
-    oid, od, oc, ost = oix.search(queries, k, order=oracle.ORDER_CANONICAL, stop=oracle.STOP_STRICT_M)
-    np.testing.assert_array_equal(oid, ids)
-    for q in range(nq):
-        assert stats["radius"][q] == ost[q]["radius"]
-        assert stats["candidates"][q] == ost[q]["candidates"]
-        if bits // m < 32:
-            assert stats["probes"][q] == ost[q]["probes"]
-        else:
-            assert stats["occupancy_tests"][q] == ost[q]["probes"]
-        assert stats["n_results"][q] == counts[q]
+    # stop rule tested per radius (0, the reference's rhythm), per table (1), or adaptively (-1, the default):
+    # the answers are always the canonical top-k; the statistics follow the oracle run with the same rhythm
+    for table_steps, ostop in ((0, oracle.STOP_STRICT_M), (1, oracle.STOP_TABLE_STRICT), (-1, None)):
+        ix.set_param("mih.table_steps", table_steps)
+        ids, dists, counts, stats = ix.search_mih(queries, k)
+        np.testing.assert_array_equal(counts, lc)
+        np.testing.assert_array_equal(dists, ld)
+        np.testing.assert_array_equal(ids, lid)
+        assert (stats["n_results"] == counts).all()
+        if ostop is None:
+            continue
+        oid, od, oc, ost = oix.search(queries, k, order=oracle.ORDER_CANONICAL, stop=ostop)
+        np.testing.assert_array_equal(oid, ids)
+        for q in range(nq):
+            assert stats["radius"][q] == ost[q]["radius"]
+            assert stats["candidates"][q] == ost[q]["candidates"]
+            if bits // m < 32:
+                assert stats["probes"][q] == ost[q]["probes"]
+            else:
+                assert stats["occupancy_tests"][q] == ost[q]["probes"]
+    gid, gd, gc = ix.search_linear(queries, k)
+    np.testing.assert_array_equal(gid, lid)
+    np.testing.assert_array_equal(gd, ld)
     ix.close()
 
 

@@ -116,7 +116,8 @@ struct vc_index {
   int64_t mih_prefilter = -1;
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
-  int64_t mih_min_bucket = 64;    // batched path when the average bucket holds at least this many codes
+  int64_t mih_min_bucket = 64;
+  int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
   int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
   int64_t profile = 0;
@@ -661,6 +662,7 @@ static int mih_per_query(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = ix->m; p.sbits = ix->sbits;
   p.BUFM = pow2_at_least(k + kMihWbuf);
   p.approximate = approximate; p.max_radius = max_radius;
+  p.table_steps = ix->mih_table_steps != 0 ? 1 : 0;
   p.tables = ix->d_tab; p.out_keys = d_out_keys; p.stats = d_stats;
   const bool ap = approximate != 0 && max_radius < 0;
   if (ix->W == 1) return ap ? launch_mih<1, true>(ix, p, st) : launch_mih<1, false>(ix, p, st);
@@ -711,7 +713,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
                o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
                o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
-               o_ctr = take(128);
+               o_ctr = take(128);   // [0] n_items [1] item_cursor [2] n_next [3] any_overflow [4] n_likely [8..9] bucket_codes
   if ((rc = ix->b_state.ensure(off))) return rc;
   if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024))) return rc;
   unsigned char* sb = (unsigned char*)ix->b_state.p;
@@ -752,9 +754,14 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   int levels = 0;
   int64_t items_total = 0;
   bool first_verify = true;
-  for (uint32_t r = 0; n_active > 0 && r <= sbits; ++r) {
-    p.radius = r; p.active = cur; p.n_active = n_active; p.next_active = nxt;
-    const uint64_t total_probes = (uint64_t)n_active * m * host_binom(sbits, r);
+  // steps: (radius r, tables [t0, t1)).  A whole radius per step, or - when most queries are about to stop - one
+  // table per step, so that the strict rule d_k <= m*r + t can end the search in the middle of a radius.
+  uint32_t r = 0, t0 = 0;
+  bool granular = ix->mih_table_steps > 0 && max_radius < 0;
+  while (n_active > 0 && r <= sbits) {
+    const uint32_t t1 = granular ? t0 + 1 : m;
+    p.radius = r; p.t_begin = t0; p.t_end = t1; p.active = cur; p.n_active = n_active; p.next_active = nxt;
+    const uint64_t total_probes = (uint64_t)n_active * (t1 - t0) * host_binom(sbits, r);
     if ((rc = ix->b_qlist.ensure(std::max<uint64_t>(total_probes, 1) * 4))) return rc;
     p.qlist = (uint32_t*)ix->b_qlist.p;
     const int pgrid = grid_for(total_probes, 256, ix->num_sms);
@@ -774,6 +781,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     if ((rc = ix->b_items.ensure(std::max<size_t>(n_items, 1) * sizeof(BmihItem)))) return rc;
     p.items = (BmihItem*)ix->b_items.p;
     CU(cudaMemsetAsync(ctr, 0, 12, st));
+    CU(cudaMemsetAsync(ctr + 4, 0, 4, st));
     bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
     const bool timed = ix->profile && levels < 34;
     if (timed) {
@@ -785,15 +793,24 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
     first_verify = false;
-    bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, 1, ctr + 3);
+    bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, 1, ctr + 3, ctr + 4);
     ix->launches += 6;
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+    uint32_t h5[5];
+    CU(cudaMemcpyAsync(h5, ctr, 20, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    n_active = h_ctr[2];
+    h_ctr[3] = h5[3];
+    const uint32_t n_likely = h5[4];
+    n_active = h5[2];
     std::swap(cur, nxt);
     ++levels;
     items_total += n_items;
+    t0 = t1;
+    if (t0 == m) {
+      t0 = 0; ++r;
+      // next radius: one table at a time if most of the remaining queries would stop inside it anyway
+      granular = max_radius < 0 && (ix->mih_table_steps > 0 || (ix->mih_table_steps < 0 && (uint64_t)n_likely * 2 >= n_active));
+    }
   }
   if (ix->profile) { ix->lev_used = std::min(levels, 34); ix->ev_valid = true; }
   (void)first_verify;
@@ -907,6 +924,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
   else if (!strcmp(name, "mih.wide")) ix->mih_wide = value;
   else if (!strcmp(name, "mih.min_bucket")) ix->mih_min_bucket = value;
+  else if (!strcmp(name, "mih.table_steps")) ix->mih_table_steps = value;
   else if (!strcmp(name, "profile")) {
     DeviceGuard g(ix->device);
     if (value && !ix->ev0) { CU(cudaEventCreate(&ix->ev0)); CU(cudaEventCreate(&ix->ev1)); }

@@ -44,7 +44,8 @@ struct BmihItem { uint32_t t, c0, c1, qbeg, qn; };
 struct BmihParams {
   const uint32_t* queries;      // [nq][2W]
   uint32_t nq, k, m, sbits;
-  uint32_t radius;              // level being processed
+  uint32_t radius;              // radius of the step being processed
+  uint32_t t_begin, t_end;      // ... and its tables [t_begin, t_end): a whole radius (0, m) or one table of it
   uint32_t cpi;                 // codes per work item (multiple of the step size)
   int max_radius;
   const TableDev* tables;       // [m]
@@ -77,12 +78,12 @@ struct BmihParams {
 template <int W>
 __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
   const uint32_t per_table = c_binom[p.sbits][p.radius];
-  const uint64_t per_q = (uint64_t)per_table * p.m;
+  const uint64_t per_q = (uint64_t)per_table * (p.t_end - p.t_begin);
   const uint64_t total = per_q * p.n_active;
   for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t a = (uint32_t)(it / per_q);
     const uint32_t rem = (uint32_t)(it % per_q);
-    const uint32_t t = rem / per_table, pidx = rem % per_table;
+    const uint32_t t = p.t_begin + rem / per_table, pidx = rem % per_table;
     const uint32_t q = p.active[a];
     const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
     const uint32_t key = qkey ^ unrank_mask(p.sbits, p.radius, pidx);
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
 // sort the candidate buffer, keep k, refresh thresholds / histogram, apply the stop rule for level `radius`
 template <int W>
 __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, int count_probes,
-                                                          uint32_t* any_overflow) {
+                                                          uint32_t* any_overflow, uint32_t* n_likely) {
   __shared__ uint64_t buf[kBmihCap];
   __shared__ uint32_t cnt;
   constexpr int HB = BmihCfg<W>::HB;
@@ -299,12 +300,21 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
     p.gtaukey[q] = tk;
     if (tk != kEmptyKey) atomicMin(&p.gtau[q], (uint32_t)(tk >> 32));
     const uint32_t r = p.radius;
-    bool stop = r >= p.sbits || (p.gflag[q] & 1u) != 0;                                  // overflowed queries are redone elsewhere
-    if (p.max_radius >= 0) stop = stop || r >= (uint32_t)p.max_radius;
-    else stop = stop || (kept == p.k && (uint32_t)(tk >> 32) + 1 <= p.m * (r + 1));      // search_worker.cc:204, strict and m-aware
+    const bool level_done = p.t_end == p.m;                                               // a whole radius is finished
+    bool stop = (p.gflag[q] & 1u) != 0;                                                   // overflowed queries are redone elsewhere
+    if (level_done) {
+      stop = stop || r >= p.sbits;
+      if (p.max_radius >= 0) stop = stop || r >= (uint32_t)p.max_radius;
+    }
+    // search_worker.cc:204, strict and m-aware: codes not found yet have substring distance >= r+1 in tables < t_end
+    // and >= r in the others, so their distance is >= m*r + t_end > d_k.  t_end == m gives d_k <= m*(r+1) - 1.
+    const uint32_t dk = (uint32_t)(tk >> 32);
+    if (p.max_radius < 0) stop = stop || (kept == p.k && dk + 1 <= p.m * r + p.t_end);
     p.gradius[q] = r;
-    if (count_probes) p.gprobes[q] += (unsigned long long)p.m * c_binom[p.sbits][r];   // n_sub_reads_ of this level
+    if (count_probes) p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][r];   // n_sub_reads_ of this step
     if (p.gflag[q] & 1u) *any_overflow = 1;
+    // would this query stop somewhere inside the next radius even if its k-th distance did not improve any more?
+    if (!stop && level_done && kept == p.k && dk + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
     if (stop) atomicOr(&p.gflag[q], 2u);
     else p.next_active[atomicAdd(p.n_next, 1u)] = q;
   }

@@ -41,6 +41,7 @@ struct MihParams {
   uint32_t BUFM;             // per-query buffer entries: power of two >= k + kMihWbuf
   int approximate;           // stop when >= 20k distinct candidates were seen (search_worker.cc:136-137)
   int max_radius;            // >= 0: fixed radius; < 0: stop rule
+  int table_steps;           // exact mode: 1 = test the stop rule after every table of a radius (d_k <= m*r + t), 0 = per radius
   const TableDev* tables;    // [m] in device memory
   uint64_t* out_keys;        // [nq][k]
   vc_query_stats* stats;     // [nq] or null
@@ -136,9 +137,13 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
   uint32_t radius = 0;
   unsigned long long my_probes = 0, my_occ = 0, my_cands = 0, my_unique = 0;
 
+  const bool tsteps = p.table_steps != 0 && !APPROX && p.max_radius < 0;
+  bool done = false;
   for (;; ++radius) {                                                // search_worker.cc:170
     const uint32_t per_table = c_binom[sbits][radius];              // C(s, r) probes per table
-    const uint64_t total = (uint64_t)per_table * m;
+   for (uint32_t t0 = 0; t0 < m && !done;) {
+    const uint32_t t1 = tsteps ? t0 + 1 : m;                         // tables [t0, t1) of this radius in one go
+    const uint64_t total = (uint64_t)per_table * (t1 - t0);
     // few probes (radius 0, 1): every warp visits every bucket and streams its own eighth of it; otherwise
     // the warps take different groups of 32 probes
     const bool split = total < (uint64_t)kMihWarps * 32 * 2;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
       const uint64_t item = g + lane;
       uint32_t bt = 0, bstart = 0, blen = 0;
       if (item < total) {
-        bt = (uint32_t)(item / per_table);
+        bt = t0 + (uint32_t)(item / per_table);
         const uint32_t pidx = (uint32_t)(item % per_table);
         const uint32_t key = s_qkey[bt] ^ unrank_mask(sbits, radius, pidx);      // :260 curr ^ (1 << len)
         table_lookup(s_tab[bt], key, bstart, blen);                             // :246 proxy get
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
         }
       }
     }
-    // ---- end of radius step: fold every warp's staging buffer, then decide ------------------------
+    // ---- end of the step: fold every warp's staging buffer, then decide ---------------------------------
     mih_flush(mbuf, v_tau_key, v_tau_dist, &s_mcnt, &s_lock, p.BUFM, k, wbuf, wcnt, lane);
     if (APPROX) {
       for (int o = 16; o > 0; o >>= 1) my_unique += __shfl_xor_sync(0xffffffffu, my_unique, o);
@@ -270,14 +275,22 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
     }
     __syncthreads();
     if (tid == 0) {
-      bool stop = radius >= sbits;                                              // :170 radius <= s
-      if (p.max_radius >= 0) stop = stop || radius >= (uint32_t)p.max_radius;
-      else if (APPROX) stop = stop || s_unique >= (unsigned long long)k * VC_APPROXIMATE_FACTOR;   // :136-137
-      else stop = stop || (s_mcnt == k && (uint32_t)(s_tau_key >> 32) + 1 <= m * (radius + 1));   // strict, m-aware (:204)
+      bool stop = false;
+      if (t1 == m) {                                                              // a whole radius is finished
+        stop = radius >= sbits;                                                   // :170 radius <= s
+        if (p.max_radius >= 0) stop = stop || radius >= (uint32_t)p.max_radius;
+        else if (APPROX) stop = stop || s_unique >= (unsigned long long)k * VC_APPROXIMATE_FACTOR;   // :136-137
+      }
+      // strict, m-aware stop rule (:204): codes not found yet have substring distance >= r+1 in tables < t1 and
+      // >= r in the others, i.e. distance >= m*r + t1 > d_k.  For t1 == m this is d_k <= m*(r+1) - 1.
+      if (!APPROX && p.max_radius < 0) stop = stop || (s_mcnt == k && (uint32_t)(s_tau_key >> 32) + 1 <= m * radius + t1);
       s_stop = stop ? 1u : 0u;
     }
     __syncthreads();
-    if (s_stop) break;
+    if (s_stop) done = true;
+    t0 = t1;
+   }
+    if (done) break;
   }
 
   // ---- results and statistics ---------------------------------------------------------------------
