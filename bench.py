@@ -196,6 +196,15 @@ def main():
     for i in range(args.warmup):
         step(i)
     barrier()
+    # self-check outside the timed region: the MIH answer of a few queries equals the brute-force scan of the same
+    # (sharded) database - bit-exact, through the same all-gather + merge
+    chk = dev_batches[0][:8].contiguous()
+    a = searcher.search(chk, K_NN, mode="mih").clone()
+    bscan = searcher.search(chk, K_NN, mode="linear").clone()
+    parity_ok = bool(torch.equal(a, bscan))
+    if not parity_ok:
+        raise SystemExit("bench.py: MIH and linear-scan results differ - refusing to report a number")
+    barrier()
     launches0 = ix.get_param("launches")
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -345,7 +354,7 @@ def main():
                        "l2": "inputs larger than L2 (tables %.1f GB per GPU, >= 300 MB touched per query)" % (ix.info()["device_bytes"] / 1e9),
                        "parallelism": "id-shard x%d, NCCL all-gather top-k merge" % world},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "integer_pipe": integer_pipe, "cpu_baseline": cpu_baseline,
-            "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
+            "parity_selfcheck": "mih == linear scan on 8 queries: %s" % parity_ok, "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
         }
         print(json.dumps(line))
     ix.close()

@@ -144,6 +144,15 @@ int vc_merge_topk_dev(int device, const uint64_t* d_lists, uint32_t n_lists, uin
 /* Host-buffer convenience form of the same merge (copies in, merges on `device`, copies out). */
 int vc_merge_topk(int device, const uint64_t* lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint64_t* out);
 
+/* Id-sharded search over several GPUs (one process per GPU): `fn` must sum, in place and over all shards, the
+ * n_words uint32 words at device address d_words (an all-reduce; enqueued on `stream` or ordered after it) and
+ * return 0.  When set, the batched MIH search calls it once per search step on its per-query distance
+ * histograms, which lets every shard filter and stop on the k-th distance of the whole database instead of its
+ * own (fewer probes per shard; all shards then take the same steps, so the collective is matched).  Replaces the
+ * per-radius MPI_Gatherv / MPI_Bcast pair of src/search_worker.cc:177,207.  fn = NULL (default): no exchange. */
+typedef int (*vc_allreduce_fn)(void* user, uint32_t* d_words, uint64_t n_words, void* stream);
+int vc_index_set_allreduce(vc_index* ix, vc_allreduce_fn fn, void* user);
+
 /* Tuning / introspection knobs (integers), e.g. "scan.prefilter", "scan.variant", "scan.waves",
  * "mih.threads".  Unknown names return VC_ERR_ARG.  vc_get_counter reads back launch counts etc. */
 int vc_index_set_param(vc_index* ix, const char* name, int64_t value);

@@ -24,7 +24,7 @@ EXPORTS = [
     "vc_index_add", "vc_index_add_device", "vc_index_add_synthetic", "vc_synth_word", "vc_index_build",
     "vc_bucket_get", "vc_code_get", "vc_occupancy_bitmap_get", "vc_search_linear", "vc_search_mih",
     "vc_search_linear_dev", "vc_search_mih_dev", "vc_merge_topk_dev", "vc_merge_topk",
-    "vc_index_set_param", "vc_index_get_param",
+    "vc_index_set_param", "vc_index_get_param", "vc_index_set_allreduce",
 ]
 
 
@@ -48,6 +48,9 @@ class IndexInfo(C.Structure):
                 ("substring_bits", C.c_uint32), ("first_id", C.c_uint32), ("device", C.c_int32), ("built", C.c_int32),
                 ("device_bytes", C.c_uint64)]
 
+
+# int fn(void* user, uint32_t* d_words, uint64_t n_words, void* stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p)
 
 _lib = None
 
@@ -82,6 +85,7 @@ def lib():
     L.vc_search_mih_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, vp, vp]
     L.vc_merge_topk_dev.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
     L.vc_merge_topk.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+    L.vc_index_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     L.vc_index_set_param.argtypes = [vp, C.c_char_p, C.c_int64]
     L.vc_index_get_param.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     _lib = L
@@ -144,6 +148,26 @@ class Index:
         inf = IndexInfo()
         check(lib().vc_index_get_info(self.h, C.byref(inf)))
         return {f: getattr(inf, f) for f, _ in IndexInfo._fields_}
+
+    def set_allreduce(self, fn):
+        """fn(device_ptr, n_words, stream) -> None must sum the n_words uint32 words at device_ptr over all shards in
+        place (see vc_index_set_allreduce); fn = None removes the hook."""
+        if fn is None:
+            self._allreduce_cb = None
+            check(lib().vc_index_set_allreduce(self.h, C.cast(None, ALLREDUCE_FN), None))
+            return
+
+        def tramp(user, ptr, n_words, stream):
+            try:
+                fn(ptr, n_words, stream)
+                return 0
+            except Exception:          # an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+
+        self._allreduce_cb = ALLREDUCE_FN(tramp)      # keep the trampoline alive as long as the index
+        check(lib().vc_index_set_allreduce(self.h, self._allreduce_cb, None))
 
     def set_param(self, name, value):
         check(lib().vc_index_set_param(self.h, name.encode(), int(value)))

@@ -117,6 +117,8 @@ struct vc_index {
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
+  vc_allreduce_fn allreduce_fn = nullptr;
+  void* allreduce_user = nullptr;
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
   int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
@@ -713,6 +715,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
                o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
                o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
+               o_xhist = take((size_t)nq * Cfg::HB * 4),
                o_ctr = take(128);   // [0] n_items [1] item_cursor [2] n_next [3] any_overflow [4] n_likely [8..9] bucket_codes
   if ((rc = ix->b_state.ensure(off))) return rc;
   if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024))) return rc;
@@ -736,12 +739,14 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
   p.gtau = (uint32_t*)(sb + o_tau); p.ghist = (uint32_t*)(sb + o_hist); p.gflag = (uint32_t*)(sb + o_flag);
   p.gradius = (uint32_t*)(sb + o_rad); p.gprobes = (unsigned long long*)(sb + o_probes); p.gcands = (unsigned long long*)(sb + o_cands);
+  uint32_t* xhist = (uint32_t*)(sb + o_xhist);
   uint32_t* actA = (uint32_t*)(sb + o_actA);
   uint32_t* actB = (uint32_t*)(sb + o_actB);
 
   // ---- start: all queries active, thresholds bootstrapped from a sample of each query's own buckets -------
   CU(cudaMemsetAsync(ctr, 0, 128, st));
   CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));      // histograms count this search's candidates only
+  CU(cudaMemsetAsync(xhist, 0, (size_t)nq * Cfg::HB * 4, st));
   bmih_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p, actA);
   bmih_bootstrap_kernel<W><<<(nq + 7) / 8, 256, 0, st>>>(p);
   ix->launches += 2;
@@ -793,8 +798,14 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
     first_verify = false;
-    bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, 1, ctr + 3, ctr + 4);
-    ix->launches += 6;
+    bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, xhist);
+    if (ix->allreduce_fn) {
+      // id-sharded search: sum the histograms over the shards, so that every GPU filters and stops on the k-th
+      // distance of the WHOLE database (and all ranks walk through the same steps)
+      if (ix->allreduce_fn(ix->allreduce_user, xhist, (uint64_t)nq * Cfg::HB, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+    }
+    bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
+    ix->launches += 7;
     CU(cudaGetLastError());
     uint32_t h5[5];
     CU(cudaMemcpyAsync(h5, ctr, 20, cudaMemcpyDeviceToHost, st));
@@ -909,6 +920,13 @@ int vc_search_mih(vc_index* ix, const void* queries, uint32_t nq, uint32_t k, in
 // ------------------------------------------------------------------------------------------------
 // knobs
 // ------------------------------------------------------------------------------------------------
+int vc_index_set_allreduce(vc_index* ix, vc_allreduce_fn fn, void* user) {
+  if (!ix) return fail(VC_ERR_ARG, "null argument");
+  ix->allreduce_fn = fn;
+  ix->allreduce_user = user;
+  return VC_OK;
+}
+
 int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   if (!ix || !name) return fail(VC_ERR_ARG, "null argument");
   if (!strcmp(name, "scan.prefilter")) ix->scan_prefilter = value;

@@ -272,17 +272,18 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
   }
 }
 
-// ---- 4. settle: per query after a level ------------------------------------------------------------------
-// sort the candidate buffer, keep k, refresh thresholds / histogram, apply the stop rule for level `radius`
+// ---- 4. settle: per query after a step --------------------------------------------------------------------
+// sort the candidate buffer, keep k, refresh the exact local threshold and the distance histogram of what is
+// kept; the histogram row is also copied to `xhist`, which the decide kernel reads - possibly after it has been
+// summed over all id-shards (GPUs) by the caller's all-reduce.
 template <int W>
-__global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, int count_probes,
-                                                          uint32_t* any_overflow, uint32_t* n_likely) {
+__global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, uint32_t* xhist) {
   __shared__ uint64_t buf[kBmihCap];
   __shared__ uint32_t cnt;
   constexpr int HB = BmihCfg<W>::HB;
   const uint32_t tid = threadIdx.x;
   if (blockIdx.x >= n_list) return;
-  const uint32_t q = list ? list[blockIdx.x] : blockIdx.x;
+  const uint32_t q = list[blockIdx.x];
   const uint32_t raw = p.gcnt[q];
   const uint32_t n = min(raw, (uint32_t)kBmihCap);
   for (uint32_t i = tid; i < n; i += 256) buf[i] = p.gbuf[(size_t)q * kBmihCap + i];
@@ -295,29 +296,50 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   for (uint32_t i = tid; i < HB; i += 256) gh[i] = 0;
   __syncthreads();
   for (uint32_t i = tid; i < kept; i += 256) atomicAdd(&gh[(uint32_t)(buf[i] >> 32)], 1u);
+  __syncthreads();
+  for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = gh[i];
   if (tid == 0) {
     p.gcnt[q] = kept;
     p.gtaukey[q] = tk;
     if (tk != kEmptyKey) atomicMin(&p.gtau[q], (uint32_t)(tk >> 32));
-    const uint32_t r = p.radius;
-    const bool level_done = p.t_end == p.m;                                               // a whole radius is finished
-    bool stop = (p.gflag[q] & 1u) != 0;                                                   // overflowed queries are redone elsewhere
-    if (level_done) {
-      stop = stop || r >= p.sbits;
-      if (p.max_radius >= 0) stop = stop || r >= (uint32_t)p.max_radius;
-    }
-    // search_worker.cc:204, strict and m-aware: codes not found yet have substring distance >= r+1 in tables < t_end
-    // and >= r in the others, so their distance is >= m*r + t_end > d_k.  t_end == m gives d_k <= m*(r+1) - 1.
-    const uint32_t dk = (uint32_t)(tk >> 32);
-    if (p.max_radius < 0) stop = stop || (kept == p.k && dk + 1 <= p.m * r + p.t_end);
-    p.gradius[q] = r;
-    if (count_probes) p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][r];   // n_sub_reads_ of this step
-    if (p.gflag[q] & 1u) *any_overflow = 1;
-    // would this query stop somewhere inside the next radius even if its k-th distance did not improve any more?
-    if (!stop && level_done && kept == p.k && dk + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
-    if (stop) atomicOr(&p.gflag[q], 2u);
-    else p.next_active[atomicAdd(p.n_next, 1u)] = q;
   }
+}
+
+// ---- 5. decide: stop rule and next active list ------------------------------------------------------------
+// xhist[q][d] = number of known database codes at distance d from query q - this shard's kept candidates, or the
+// sum over all shards.  tau = smallest d with at least k codes at distance <= d bounds the final k-th distance
+// (of the whole database when summed), so it both tightens the filter and decides the stop: codes not found yet
+// have substring distance >= r+1 in tables < t_end and >= r in the others, i.e. distance >= m*r + t_end, and the
+// search can end as soon as that exceeds tau (search_worker.cc:204 made strict and m-aware; t_end == m gives
+// the per-radius form d_k <= m*(r+1) - 1).  With summed histograms every shard takes the same decisions.
+template <int W>
+__global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, const uint32_t* xhist,
+                                   uint32_t* any_overflow, uint32_t* n_likely) {
+  constexpr int HB = BmihCfg<W>::HB;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  const uint32_t q = list[i];
+  uint32_t tau = kInfDist, cum = 0;
+  for (uint32_t d = 0; d <= 64 * W; ++d) {
+    cum += xhist[(size_t)q * HB + d];
+    if (cum >= p.k) { tau = d; break; }
+  }
+  if (tau != kInfDist) atomicMin(&p.gtau[q], tau);
+  const uint32_t r = p.radius;
+  const bool level_done = p.t_end == p.m;                                                // a whole radius is finished
+  bool stop = false;
+  if (level_done) {
+    stop = r >= p.sbits;
+    if (p.max_radius >= 0) stop = stop || r >= (uint32_t)p.max_radius;
+  }
+  if (p.max_radius < 0) stop = stop || (tau != kInfDist && tau + 1 <= p.m * r + p.t_end);
+  p.gradius[q] = r;
+  p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][r];      // n_sub_reads_ of this step
+  if (p.gflag[q] & 1u) *any_overflow = 1;                                                // buffer overflowed: redone by the per-query kernel
+  // would this query stop somewhere inside the next radius even if tau did not improve any more?
+  if (!stop && level_done && tau != kInfDist && tau + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
+  if (stop) atomicOr(&p.gflag[q], 2u);
+  else p.next_active[atomicAdd(p.n_next, 1u)] = q;
 }
 
 // per-query state at the start of a search

@@ -8,7 +8,11 @@ flag once per radius step (src/mpi_coordinator.cc:26-69, src/search_worker.cc:17
   * queries are replicated; every rank answers them on its shard (exact local top-k; the MIH stop rule
     is applied per shard, so no collective inside the radius loop);
   * ONE all-gather of [nq][k] packed words (dist<<32|id) per batch over NVLink, then every rank folds
-    the G lists with merge_topk_kernel (shards are id-disjoint, so no de-duplication is needed).
+    the G lists with merge_topk_kernel (shards are id-disjoint, so no de-duplication is needed);
+  * inside the MIH search, one small all-reduce per search step sums the per-query distance histograms of
+    the shards (vc_index_set_allreduce), so that every GPU filters and stops on the k-th distance of the
+    WHOLE database: a shard then does 1/G of the single-GPU work instead of searching to its own, larger,
+    local k-th distance.  (The reference exchanges all candidates and a stop flag per radius step.)
 
 torch.distributed is plumbing here (process group, the all-gather, device buffers); searching and
 merging are the library's CUDA kernels, called through the C ABI with raw device pointers.
@@ -38,7 +42,7 @@ class ShardedSearcher:
     `gloo` backend by overriding them; the product path always runs the CUDA kernels.
     """
 
-    def __init__(self, index, group=None):
+    def __init__(self, index, group=None, global_threshold=True):
         import torch
         import torch.distributed as dist
 
@@ -48,6 +52,21 @@ class ShardedSearcher:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs = {}
+        self._views = {}
+        if self.world > 1 and global_threshold and hasattr(index, "set_allreduce"):
+            index.set_allreduce(self._allreduce_words)
+
+    def _allreduce_words(self, ptr, n_words, stream):
+        """Sum n_words int32 words at device address ptr over the ranks (NCCL), ordered after `stream`."""
+        t = self.torch
+        key = (ptr, n_words)
+        view = self._views.get(key)
+        if view is None:
+            class _Raw:            # zero-copy view of library-owned device memory
+                __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+            view = t.as_tensor(_Raw(), device=t.device("cuda", self.index.device))
+            self._views = {key: view}
+        self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
 
     def _buffers(self, nq, k, device):
         key = (nq, k, str(device))
