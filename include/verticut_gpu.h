@@ -119,7 +119,8 @@ int vc_search_linear(vc_index* ix, const void* queries, uint32_t nq, uint32_t k,
 
 /* MIH search: SearchWorker::find (src/search_worker.cc:65-89) for a batch.
  *  approximate = 0: exact k-NN (search_worker.cc:159-218) with the m-aware strict stop rule
- *                   d_k <= m*(r+1) - 1 (results identical to vc_search_linear);
+ *                   d_k <= m*(r+1) - 1, by default also tested after every table t of a radius as
+ *                   d_k <= m*r + t ("mih.table_steps"); results identical to vc_search_linear;
  *  approximate = 1: search_worker.cc:93-157 - stop at the first radius that has seen
  *                   >= 20*k distinct candidates, return the k best seen;
  *  max_radius >= 0: fixed-radius mode - search radii 0..max_radius, return the k best seen
@@ -129,8 +130,9 @@ int vc_search_mih(vc_index* ix, const void* queries, uint32_t nq, uint32_t k, in
 
 /* ---- search, device buffers (multi-GPU plumbing and zero-copy callers) ----------------------
  * d_queries / d_out_keys live on the index's device; d_out_keys is [nq][k] packed words
- * (VC_EMPTY_KEY padded), ascending.  `stream` is a cudaStream_t (NULL = default stream); the
- * call only enqueues work.  d_stats may be NULL. */
+ * (VC_EMPTY_KEY padded), ascending.  `stream` is a cudaStream_t (NULL = default stream).  The linear
+ * scan only enqueues work; the MIH search walks its radius steps from the host and synchronises the
+ * stream between them (it reads back a few counters per step).  d_stats may be NULL. */
 int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, void* stream);
 int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
                       uint64_t* d_out_keys, vc_query_stats* d_stats, void* stream);

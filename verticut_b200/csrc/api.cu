@@ -101,7 +101,7 @@ struct vc_index {
   size_t smem_optin = 0;
   // scratch
   DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small, d_gstate;
-  DevBuf b_state, b_buckets, b_qlist, b_items, b_keys0, b_stats0, b_redo;   // batched MIH
+  DevBuf b_state, b_buckets, b_qlist, b_items, b_redo;   // batched MIH
   PinBuf h_q, h_ids, h_dists, h_counts, h_stats, h_small;
   // knobs
   int64_t scan_prefilter = -1;    // -1 auto, 0 off, 1 on
@@ -211,7 +211,7 @@ void vc_index_destroy(vc_index* ix) {
   if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
   for (cudaEvent_t e : ix->lev) if (e) cudaEventDestroy(e);
   DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate,
-                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_keys0, &ix->b_stats0, &ix->b_redo};
+                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_redo};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
   for (PinBuf* b : pb) b->release();
