@@ -129,16 +129,18 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
 }
 
 // ---- 3. verification ---------------------------------------------------------------------------------------
-// rare path: a code whose exact distance d passed tau of query qid
+// rare path: a code whose exact distance d passed the staged threshold tau_s of query qid.
+// ghist[q][b] holds CUMULATIVE counts: distinct known codes at distance <= b (maintained for b below the
+// threshold only - bins at or above it are never consulted again, since thresholds only fall).
 template <int W>
 __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
-                                         CodeRegs<W> c, const uint32_t* qw /* shared */) {
+                                         CodeRegs<W> c, uint32_t* qrec /* shared: query words, then tau */, uint32_t tau_s) {
   const BmihParams& p = *pp;
   // first-discoverer test: table t found this code at substring distance exactly `radius`; it is emitted here
   // only if no other table found it at a smaller distance, or at the same distance with a lower table id
   uint32_t x[2 * W];
 #pragma unroll
-  for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qw[i];
+  for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qrec[i];
   for (uint32_t t2 = 0; t2 < p.m; ++t2) {
     if (t2 == t) continue;
     const uint32_t sd = __popc(substring<W>(x, t2, p.sbits));
@@ -150,21 +152,16 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
   if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
   else atomicOr(&p.gflag[qid], 1u);
   constexpr int HB = BmihCfg<W>::HB;
-  uint32_t* gh = p.ghist + (size_t)qid * HB;
-  atomicAdd(&gh[d], 1u);
-  const uint32_t tau = __ldcg(&p.gtau[qid]);
-  if (d < tau) {
-    uint32_t cum = 0;
-    const uint32_t lim = min(tau, (uint32_t)HB);
-    for (uint32_t b0 = 0; b0 < lim; b0 += 4) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(gh + b0));
-      const uint32_t e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        cum += e[u];
-        if (cum >= p.k && b0 + u < lim) { atomicMin(&p.gtau[qid], b0 + u); return; }
-      }
-    }
+  uint32_t* gc = p.ghist + (size_t)qid * HB;
+  const uint32_t lim = min(tau_s, (uint32_t)(64 * W + 1));      // bins d .. lim-1 count this code
+  if (d >= lim) return;
+  for (uint32_t b0 = d; b0 + 1 < lim; ++b0) atomicAdd(&gc[b0], 1u);              // fire and forget
+  const uint32_t old = atomicAdd(&gc[lim - 1], 1u);
+  if (old + 1 >= p.k) {                                        // k codes are now strictly inside the threshold
+    uint32_t nt = lim - 1;
+    while (nt > 0 && __ldcg(&gc[nt - 1]) >= p.k) --nt;
+    atomicMin(&p.gtau[qid], nt);
+    atomicMin(&qrec[2 * W], nt);
   }
 }
 
@@ -243,6 +240,11 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
     __syncwarp();
     for (uint32_t base = a0; base < c1; base += WSTEP) {
       if (base != a0) load_step(base);
+      // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
+      // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
+      // of the codes down the slow path.  The load is issued here and consumed after this step's math.
+      uint32_t fresh_tau = kInfDist;
+      if (lane < qn) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
       QRec<W> nxt = load_qrec<W, QS>(s_qrec, 0);
 #pragma unroll 1
       for (uint32_t q = 0; q < qn; ++q) {
@@ -263,11 +265,14 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
             if (mm[c] <= tau) {
               const uint32_t d = PREFILTER ? hamming_exact<W>(code[c].w, qw) : mm[c];
               const uint32_t j = base + local_of(c);
-              if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[q], t, d, j, code[c], s_qrec + q * QS);
+              if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[q], t, d, j, code[c], s_qrec + q * QS, tau);
             }
           }
         }
       }
+      __syncwarp();
+      if (lane < qn && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
+      __syncwarp();
     }
   }
 }
@@ -292,12 +297,19 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   const uint64_t tk = topk_compact(buf, &cnt, kBmihCap, p.k, tid, 256, BlockSync());
   const uint32_t kept = cnt;
   for (uint32_t i = tid; i < kept; i += 256) p.gbuf[(size_t)q * kBmihCap + i] = buf[i];
-  uint32_t* gh = p.ghist + (size_t)q * HB;
-  for (uint32_t i = tid; i < HB; i += 256) gh[i] = 0;
+  // per-distance histogram of what is kept -> xhist (for the decide kernel / the cross-shard sum); its prefix
+  // sums -> ghist (the cumulative counts the append path maintains)
+  __shared__ uint32_t sh[HB];
+  for (uint32_t i = tid; i < HB; i += 256) sh[i] = 0;
   __syncthreads();
-  for (uint32_t i = tid; i < kept; i += 256) atomicAdd(&gh[(uint32_t)(buf[i] >> 32)], 1u);
+  for (uint32_t i = tid; i < kept; i += 256) atomicAdd(&sh[(uint32_t)(buf[i] >> 32)], 1u);
   __syncthreads();
-  for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = gh[i];
+  for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = sh[i];
+  if (tid == 0) {
+    uint32_t* gc = p.ghist + (size_t)q * HB;
+    uint32_t cum = 0;
+    for (uint32_t d = 0; d < HB; ++d) { cum += sh[d]; gc[d] = cum; }
+  }
   if (tid == 0) {
     p.gcnt[q] = kept;
     p.gtaukey[q] = tk;
