@@ -127,6 +127,7 @@ struct vc_index {
   bool ev_valid = false;
   cudaEvent_t lev[2 * 34] = {nullptr};   // batched MIH: one (start, stop) pair per radius level around the verify kernel
   int lev_used = 0;                        // > 0: last search was batched, sum these pairs
+  std::vector<int64_t> step_codes, step_pairs;   // per step of the last batched search: codes of distinct probed buckets, code-query tests
   // counters
   int64_t launches = 0;           // kernels launched by this index since creation
   int64_t last_scan_grid = 0, last_scan_qt = 0, last_scan_slices = 0, last_scan_smem = 0, last_scan_occ = 0, last_scan_stages = 0;
@@ -590,7 +591,7 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   if (rc) return rc;
   occ = std::max(occ, 1);
   const uint64_t capacity = (uint64_t)occ * ix->num_sms;
-  const uint64_t waves = ix->scan_waves > 0 ? (uint64_t)ix->scan_waves : ((uint64_t)p.n_qtiles * 8 <= capacity ? 1 : 8);
+  const uint64_t waves = ix->scan_waves > 0 ? (uint64_t)ix->scan_waves : ((uint64_t)p.n_qtiles * 32 <= capacity ? 1 : 8);
   const uint64_t n_steps = std::max<uint64_t>(1, (ix->n + step - 1) / step);
   // one wave: never spill a few CTAs into a second, almost empty wave (round down); several waves: round up
   uint64_t slices = waves == 1 ? std::max<uint64_t>(1, capacity / p.n_qtiles)
@@ -736,6 +737,9 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   uint32_t* scan_sums = p.boffs + n_buckets + 1 + 3;
   p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
   p.bucket_codes = (unsigned long long*)(ctr + 8);
+  p.pair_count = (unsigned long long*)(ctr + 10);
+  unsigned long long prev_codes = 0, prev_pairs = 0;
+  ix->step_codes.clear(); ix->step_pairs.clear();
   p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
   p.gtau = (uint32_t*)(sb + o_tau); p.ghist = (uint32_t*)(sb + o_hist); p.gflag = (uint32_t*)(sb + o_flag);
   p.gradius = (uint32_t*)(sb + o_rad); p.gprobes = (unsigned long long*)(sb + o_probes); p.gcands = (unsigned long long*)(sb + o_cands);
@@ -807,9 +811,15 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
     ix->launches += 7;
     CU(cudaGetLastError());
-    uint32_t h5[5];
-    CU(cudaMemcpyAsync(h5, ctr, 20, cudaMemcpyDeviceToHost, st));
+    uint32_t h5[12];
+    CU(cudaMemcpyAsync(h5, ctr, 48, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    {
+      unsigned long long cc, pp;
+      memcpy(&cc, h5 + 8, 8); memcpy(&pp, h5 + 10, 8);
+      ix->step_codes.push_back((int64_t)(cc - prev_codes)); ix->step_pairs.push_back((int64_t)(pp - prev_pairs));
+      prev_codes = cc; prev_pairs = pp;
+    }
     h_ctr[3] = h5[3];
     const uint32_t n_likely = h5[4];
     n_active = h5[2];
@@ -973,6 +983,22 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;
   else if (!strcmp(name, "mih.last_items")) *value = ix->last_mih_items;
   else if (!strcmp(name, "mih.last_bucket_codes")) *value = ix->last_mih_bucket_codes;
+  else if (!strncmp(name, "mih.step_codes.", 15) || !strncmp(name, "mih.step_pairs.", 15) || !strncmp(name, "mih.step_ns.", 12)) {
+    // per-step accounting of the last batched search: mih.step_codes.<i>, mih.step_pairs.<i>, mih.step_ns.<i> (verify kernel time)
+    const bool is_ns = name[9] == 'n';
+    const int i = atoi(name + (is_ns ? 12 : 15));
+    if (i < 0 || i >= (int)ix->step_codes.size()) return fail(VC_ERR_ARG, "step %d out of range", i);
+    if (name[9] == 'c') *value = ix->step_codes[i];
+    else if (name[9] == 'p') *value = ix->step_pairs[i];
+    else {
+      if (!ix->profile || i >= ix->lev_used) return fail(VC_ERR_STATE, "profiling is off");
+      DeviceGuard g(ix->device);
+      float ms = 0.f;
+      CU(cudaEventSynchronize(ix->lev[2 * i + 1]));
+      CU(cudaEventElapsedTime(&ms, ix->lev[2 * i], ix->lev[2 * i + 1]));
+      *value = (int64_t)((double)ms * 1e6);
+    }
+  }
   else if (!strcmp(name, "profile")) *value = ix->profile;
   else if (!strcmp(name, "last_kernel_ns")) {
     // device time of the dominant kernel (scan_topk / mih_search) of the last search; waits for it

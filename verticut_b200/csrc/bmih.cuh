@@ -57,7 +57,8 @@ struct BmihParams {
   uint32_t* qlist;              // [total probes] query index per (bucket, slot)
   BmihItem* items;
   uint32_t* n_items;            // [1]
-  unsigned long long* bucket_codes;   // [1] codes of all distinct probed buckets, summed over levels (traffic accounting)
+  unsigned long long* bucket_codes;   // [1] codes of all distinct probed buckets, summed over the steps (traffic accounting)
+  unsigned long long* pair_count;     // [1] code-query tests = members of all probed buckets over all queries, summed over the steps
   uint32_t* item_cursor;        // [1]
   // per-query state
   uint64_t* gbuf;               // [nq][kBmihCap]
@@ -91,7 +92,7 @@ __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
     const uint32_t len = rp[key + 1] - rp[key];
     const uint32_t b = (t << p.sbits) + key;
     if (pass == 0) {
-      if (len) { atomicAdd(&p.bcount[b], 1u); atomicAdd(&p.gcands[q], (unsigned long long)len); }
+      if (len) { atomicAdd(&p.bcount[b], 1u); atomicAdd(&p.gcands[q], (unsigned long long)len); atomicAdd(p.pair_count, (unsigned long long)len); }
     } else if (len) {
       const uint32_t slot = atomicAdd(&p.bcount[b], 1u);
       p.qlist[p.boffs[b] + slot] = q;
