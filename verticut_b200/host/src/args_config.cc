@@ -16,6 +16,7 @@ int image_total = 100000000;
 int knn = 10;
 int approximate = 0;
 int max_queries = 200;
+int query_image_id = -1;
 
 static struct option long_options[] = {
     {"server", required_argument, 0, 's'},      {"config_path", required_argument, 0, 'c'},
@@ -35,6 +36,7 @@ void usage() {
   printf("-i : The number of images the server has (upper bound on the codes read).\n");
   printf("-k : Find k nearest neighbors.\n");
   printf("-a : approximate search (factor 20).\n");
+  printf("-I : image id to query by (byid mode).\n");
   printf("-r : The read mode (accepted for compatibility, Pilaf only).\n");
   printf("--help -h : help information.\n");
   exit(-1);
@@ -43,7 +45,7 @@ void usage() {
 void configure(int argc, char* argv[]) {
   int opt, opt_index = 0;
   optind = 1;
-  while ((opt = getopt_long(argc, argv, "c:b:r:n:s:i:k:f:q:ah", long_options, &opt_index)) != -1) {
+  while ((opt = getopt_long(argc, argv, "c:b:r:n:s:i:k:f:q:I:ah", long_options, &opt_index)) != -1) {
     switch (opt) {
       case 'n': n_tables = atoi(optarg); break;
       case 's': server = optarg; break;
@@ -55,6 +57,7 @@ void configure(int argc, char* argv[]) {
       case 'f': binary_file = optarg; break;
       case 'q': query_file = optarg; break;
       case 'a': approximate = 1; break;
+      case 'I': query_image_id = atoi(optarg); break;
       default: usage();
     }
   }

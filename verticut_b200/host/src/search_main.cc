@@ -3,6 +3,8 @@
 //   image-search linear    -f codes -q queries ...
 //   image-search accuracy  -f codes -q queries ...      (reference: src/accuracy_test.cc)
 //   image-search integrity -f codes ...                 (reference: src/integrity_check.cc)
+//   image-search byid      -f codes -I <image id> ...   (reference: search_image_by_id, src/image_search_client.h:23-25;
+//                                                        the query-by-id branch of src/distributed_image_search.cc:95-117)
 // Output formats follow the reference: result lines "id : dist" (what image_search_server.cc:94 parses), the
 // averaged statistics line of src/distributed_image_search.cc:87-93, and for the scan
 // "Find image with id=%d and hamming_dist=%d" (src/linear_search.cc:62).  Neighbours are listed in descending
@@ -17,6 +19,7 @@
 
 #include "args_config.h"
 #include "gpu_search_worker.h"
+#include "image_search_client.h"
 #include "integrity.h"
 
 static double now() { timeval t; gettimeofday(&t, 0); return t.tv_sec + t.tv_usec * 1e-6; }
@@ -44,6 +47,20 @@ int main(int argc, char* argv[]) {
   if (proxy.finalize() != 0) { fprintf(stderr, "build failed: %s\n", proxy.last_error()); return 1; }
   double t_connect = now() - t0;
   if (!strcmp(mode, "integrity")) return run_integrity(&proxy);
+  if (!strcmp(mode, "byid")) {
+    if (query_image_id < 0) { fprintf(stderr, "an image id is required (-I)\n"); return 1; }
+    image_search_client client(&proxy);
+    try {
+      std::list<std::pair<uint32_t, uint32_t> > r = client.search_image_by_id((uint32_t)query_image_id, knn, approximate != 0);
+      for (std::list<std::pair<uint32_t, uint32_t> >::iterator it = r.begin(); it != r.end(); ++it)
+        std::cout << it->first << " : " << it->second << std::endl;      // the format image_search_server.cc:94 parses
+    } catch (const std::exception& e) {
+      fprintf(stderr, "%s\n", e.what());
+      return 1;
+    }
+    proxy.close();
+    return 0;
+  }
   if (!query_file) { fprintf(stderr, "a query file is required (-q)\n"); return 1; }
   std::vector<char> queries = read_queries(query_file, rec, max_queries);
   const size_t nq = queries.size() / rec;
