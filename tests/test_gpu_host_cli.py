@@ -67,3 +67,18 @@ def test_build_tables_via_baseproxy_put(tmp_path, oracle):
     assert "images : %d" % n in out and "%d images, 0 errors" % n in out
     out = _run([os.path.join(BIN, "build-tables"), "--check", "-f", cf, "-b", "64", "-n", "4"])
     assert "%d images, 0 errors" % n in out
+
+
+def test_cli_query_by_id(tmp_path, oracle):
+    # search_image_by_id of the reference's image_search_client, served from the GPU index (main table kept)
+    n, k = 20_000, 10
+    codes, _, cf, _ = _files(tmp_path, oracle, n, 64, 1)
+    qid = 1234
+    out = _run([os.path.join(BIN, "image-search"), "byid", "-f", cf, "-I", str(qid), "-b", "64", "-n", "4", "-k", str(k)])
+    pairs = [(int(a), int(b)) for a, b in re.findall(r"^(\d+) : (\d+)$", out, flags=re.M)]
+    oid, od, oc = oracle.linear_search(codes, codes[qid:qid + 1], k)
+    assert pairs == list(zip(oid[0][::-1].tolist(), od[0][::-1].tolist()))
+    assert pairs[-1] == (qid, 0)                                  # the image itself is its own nearest neighbour
+    res = subprocess.run([os.path.join(BIN, "image-search"), "byid", "-f", cf, "-I", str(n + 5), "-b", "64", "-n", "4"],
+                         capture_output=True, text=True)
+    assert res.returncode != 0 and "Can't find match" in res.stderr
