@@ -7,8 +7,9 @@ Step   : one batch of Q queries answered exactly by the MIH path (m = 4 tables) 
          (N > 1) by one NCCL all-gather of the local top-k and the merge kernel.
 value  : whole-job queries/s with the query batch already resident in HBM.
 e2e    : the same through the host-buffer call (vc_search_mih, pinned staging, H2D + D2H inside the timed region).
-roofline: dominant kernel (mih_search_kernel) - algorithmic bytes / CUDA-event time,
-         against the measured HBM peak of MEASURED_PEAKS.json.
+roofline: dominant kernel (bmih_verify_kernel, all launches of a search) - algorithmic bytes /
+         CUDA-event time against the measured HBM peak of MEASURED_PEAKS.json; roofline.combined = the slower of HBM
+         time and POPC time per search step, summed, over the measured time; integer_pipe = tests/s vs POPC peak.
 scan   : the brute-force path (config C4): passes/s at small batches as HBM GB/s vs peak, queries/s at a large batch.
 cpu_baseline: the reference's own linear scan (oracle/_ref, unmodified sources) on a bounded sample, host cores.
 
