@@ -98,6 +98,12 @@ uint64_t vc_synth_word(uint64_t seed, uint64_t id, uint32_t word);
  * generate_bitmap (src/generate_bitmap.cc:99-125).  Bucket members end up in ascending id order. */
 int vc_index_build(vc_index* ix);
 
+/* Index persistence: the reference keeps its tables in external KV servers, so a search process finds them
+ * built; here they live in the HBM of the process, so they can be written to / read from a file instead
+ * (codes, all tables, occupancy bitmaps; little-endian, versioned header).  vc_index_load creates the index. */
+int vc_index_save(vc_index* ix, const char* path);
+int vc_index_load(int device, const char* path, vc_index** out);
+
 /* ---- BaseProxy::get -------------------------------------------------------------------- */
 /* get(HashIndex{table,index}, Image_List) (src/base_proxy.h:18, src/search_worker.cc:246): copies up
  * to `cap` members (ids and/or codes may be NULL) in stored order; *n = bucket size.

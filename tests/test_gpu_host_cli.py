@@ -82,3 +82,18 @@ def test_cli_query_by_id(tmp_path, oracle):
     res = subprocess.run([os.path.join(BIN, "image-search"), "byid", "-f", cf, "-I", str(n + 5), "-b", "64", "-n", "4"],
                          capture_output=True, text=True)
     assert res.returncode != 0 and "Can't find match" in res.stderr
+
+
+def test_cli_build_once_search_from_index_file(tmp_path, oracle):
+    # build-tables -o writes the index; the search tool reads it with -x instead of rebuilding from the code file
+    n, nq, k = 20_000, 3, 10
+    codes, queries, cf, qf = _files(tmp_path, oracle, n, 64, nq)
+    idx = str(tmp_path / "tables.vc")
+    _run([os.path.join(BIN, "build-tables"), "-f", cf, "-b", "64", "-n", "4", "-o", idx])
+    out = _run([os.path.join(BIN, "image-search"), "mih", "-x", idx, "-q", qf, "-b", "64", "-n", "4", "-k", str(k)])
+    oid, od, oc = oracle.linear_search(codes, queries, k)
+    blocks = re.split(r"query \d+\n", out)[1:]
+    assert len(blocks) == nq
+    for q, blk in enumerate(blocks):
+        pairs = [(int(a), int(b)) for a, b in re.findall(r"^(\d+) : (\d+)$", blk, flags=re.M)]
+        assert pairs == list(zip(oid[q][::-1].tolist(), od[q][::-1].tolist()))

@@ -24,7 +24,7 @@ EXPORTS = [
     "vc_index_add", "vc_index_add_device", "vc_index_add_synthetic", "vc_synth_word", "vc_index_build",
     "vc_bucket_get", "vc_code_get", "vc_occupancy_bitmap_get", "vc_search_linear", "vc_search_mih",
     "vc_search_linear_dev", "vc_search_mih_dev", "vc_merge_topk_dev", "vc_merge_topk",
-    "vc_index_set_param", "vc_index_get_param", "vc_index_set_allreduce",
+    "vc_index_set_param", "vc_index_get_param", "vc_index_set_allreduce", "vc_index_save", "vc_index_load",
 ]
 
 
@@ -76,6 +76,8 @@ def lib():
     L.vc_index_add_device.argtypes = [vp, vp, C.c_uint64]
     L.vc_index_add_synthetic.argtypes = [vp, C.c_uint64, C.c_uint64]
     L.vc_index_build.argtypes = [vp]
+    L.vc_index_save.argtypes = [vp, C.c_char_p]
+    L.vc_index_load.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
     L.vc_bucket_get.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, u32p]
     L.vc_code_get.argtypes = [vp, C.c_uint32, vp]
     L.vc_occupancy_bitmap_get.argtypes = [vp, C.c_uint32, vp, C.c_uint64]
@@ -118,6 +120,20 @@ class Index:
         self.code_bits, self.n_tables, self.device, self.first_id = code_bits, n_tables, device, first_id
         self.nbytes = code_bits // 8
         check(lib().vc_index_create(device, code_bits, n_tables, first_id, C.byref(self.h)))
+
+    def save(self, path):
+        check(lib().vc_index_save(self.h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path, device=0):
+        """Reads an index written by save(); the tables come back built."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        check(lib().vc_index_load(device, os.fsencode(path), C.byref(self.h)))
+        inf = self.info()
+        self.code_bits, self.n_tables, self.device, self.first_id = inf["code_bits"], inf["n_tables"], device, inf["first_id"]
+        self.nbytes = self.code_bits // 8
+        return self
 
     def close(self):
         if self.h:

@@ -414,6 +414,111 @@ int vc_index_build(vc_index* ix) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// persistence
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct FileHeader {
+  char magic[8];                 // "VCIX0001"
+  uint32_t bits, m, sbits, first_id;
+  uint64_t n;
+};
+struct TableHeader { uint32_t sparse, n_unique; uint64_t row_ptr_entries; };
+const size_t kIoChunk = (size_t)64 << 20;
+
+int dev_to_file(FILE* f, const void* d, size_t bytes, std::vector<char>& stage) {
+  for (size_t off = 0; off < bytes; off += kIoChunk) {
+    const size_t nb = std::min(kIoChunk, bytes - off);
+    CU(cudaMemcpy(stage.data(), (const char*)d + off, nb, cudaMemcpyDeviceToHost));
+    if (fwrite(stage.data(), 1, nb, f) != nb) return fail(VC_ERR_STATE, "short write");
+  }
+  return VC_OK;
+}
+int file_to_dev(FILE* f, void* d, size_t bytes, std::vector<char>& stage) {
+  for (size_t off = 0; off < bytes; off += kIoChunk) {
+    const size_t nb = std::min(kIoChunk, bytes - off);
+    if (fread(stage.data(), 1, nb, f) != nb) return fail(VC_ERR_STATE, "short read (truncated index file)");
+    CU(cudaMemcpy((char*)d + off, stage.data(), nb, cudaMemcpyHostToDevice));
+  }
+  return VC_OK;
+}
+}  // namespace
+
+int vc_index_save(vc_index* ix, const char* path) {
+  if (!ix || !path) return fail(VC_ERR_ARG, "null argument");
+  if (ix->m && !ix->built) return fail(VC_ERR_STATE, "tables are not built");
+  DeviceGuard g(ix->device);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(VC_ERR_ARG, "cannot open %s for writing", path);
+  std::vector<char> stage(kIoChunk);
+  FileHeader h;
+  memcpy(h.magic, "VCIX0001", 8);
+  h.bits = ix->bits; h.m = ix->m; h.sbits = ix->sbits; h.first_id = ix->first_id; h.n = ix->n;
+  int rc = fwrite(&h, sizeof h, 1, f) == 1 ? VC_OK : fail(VC_ERR_STATE, "short write");
+  if (!rc && ix->n) rc = dev_to_file(f, ix->d_codes, ix->n * ix->W * 8, stage);
+  for (uint32_t t = 0; t < ix->m && !rc; ++t) {
+    const TableDev& T = ix->tab[t];
+    TableHeader th;
+    th.sparse = T.sparse; th.n_unique = T.n_unique;
+    th.row_ptr_entries = T.sparse ? (uint64_t)T.n_unique + 1 : (1ull << ix->sbits) + 1;
+    if (fwrite(&th, sizeof th, 1, f) != 1) { rc = fail(VC_ERR_STATE, "short write"); break; }
+    rc = dev_to_file(f, T.row_ptr, th.row_ptr_entries * 4, stage);
+    if (!rc && T.sparse) rc = dev_to_file(f, T.bitmap, (1ull << (ix->sbits - 5)) * 4, stage);
+    if (!rc && T.sparse) rc = dev_to_file(f, T.rank_dir, ((1ull << ix->sbits) / kRankBlockBits) * 4, stage);
+    if (!rc && ix->n) rc = dev_to_file(f, T.ids, ix->n * 4, stage);
+    if (!rc && ix->n) rc = dev_to_file(f, T.codes, ix->n * ix->W * 8, stage);
+  }
+  if (fclose(f) != 0 && !rc) rc = fail(VC_ERR_STATE, "close failed");
+  return rc;
+}
+
+int vc_index_load(int device, const char* path, vc_index** out) {
+  if (!path || !out) return fail(VC_ERR_ARG, "null argument");
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(VC_ERR_ARG, "cannot open %s", path);
+  FileHeader h;
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "VCIX0001", 8) != 0) { fclose(f); return fail(VC_ERR_ARG, "%s is not a verticut index file", path); }
+  vc_index* ix = nullptr;
+  int rc = vc_index_create(device, h.bits, h.m, h.first_id, &ix);
+  if (rc) { fclose(f); return rc; }
+  if (ix->sbits != h.sbits) { fclose(f); vc_index_destroy(ix); return fail(VC_ERR_ARG, "corrupt header"); }
+  DeviceGuard g(device);
+  std::vector<char> stage(kIoChunk);
+  rc = reserve_codes(ix, std::max<uint64_t>(h.n, 1));
+  if (!rc && h.n) rc = file_to_dev(f, ix->d_codes, h.n * ix->W * 8, stage);
+  ix->n = h.n;
+  auto dmalloc = [&](void** p, size_t bytes) -> int { CU(cudaMalloc(p, bytes)); ix->table_bytes += bytes; return VC_OK; };
+  const uint64_t nalloc = std::max<uint64_t>(h.n, 1);
+  for (uint32_t t = 0; t < h.m && !rc; ++t) {
+    TableDev& T = ix->tab[t];
+    TableHeader th;
+    if (fread(&th, sizeof th, 1, f) != 1) { rc = fail(VC_ERR_STATE, "short read (truncated index file)"); break; }
+    const uint64_t expect = th.sparse ? (uint64_t)th.n_unique + 1 : (1ull << h.sbits) + 1;
+    if (th.row_ptr_entries != expect || (th.sparse != 0) != (h.sbits > 16)) { rc = fail(VC_ERR_ARG, "corrupt table header"); break; }
+    T.sparse = th.sparse; T.n_unique = th.n_unique;
+    if ((rc = dmalloc((void**)&T.row_ptr, th.row_ptr_entries * 4))) break;
+    if ((rc = file_to_dev(f, T.row_ptr, th.row_ptr_entries * 4, stage))) break;
+    if (T.sparse) {
+      const uint64_t nwords = 1ull << (h.sbits - 5), nrb = (1ull << h.sbits) / kRankBlockBits;
+      if ((rc = dmalloc((void**)&T.bitmap, nwords * 4)) || (rc = file_to_dev(f, T.bitmap, nwords * 4, stage))) break;
+      if ((rc = dmalloc((void**)&T.rank_dir, nrb * 4)) || (rc = file_to_dev(f, T.rank_dir, nrb * 4, stage))) break;
+    }
+    if ((rc = dmalloc((void**)&T.ids, (nalloc + 64) * 4)) || (rc = dmalloc((void**)&T.codes, (nalloc + 64) * ix->W * 8))) break;
+    if (h.n && ((rc = file_to_dev(f, T.ids, h.n * 4, stage)) || (rc = file_to_dev(f, T.codes, h.n * ix->W * 8, stage)))) break;
+  }
+  fclose(f);
+  if (!rc && h.m) {
+    cudaError_t e = cudaMalloc(&ix->d_tab, sizeof(TableDev) * kMaxTables);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->d_tab, ix->tab, sizeof(TableDev) * kMaxTables, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail(VC_ERR_CUDA, "table descriptors: %s", cudaGetErrorString(e));
+  }
+  if (rc) { vc_index_destroy(ix); return rc; }
+  ix->built = true;
+  *out = ix;
+  return VC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // BaseProxy::get
 // ------------------------------------------------------------------------------------------------
 int vc_bucket_get(vc_index* ix, uint32_t table, uint32_t index, uint32_t* ids, void* codes, uint32_t cap, uint32_t* n_out) {

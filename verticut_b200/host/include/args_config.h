@@ -15,6 +15,8 @@ extern int image_total;           // 100000000; upper bound on the codes read fr
 extern int knn;                   // 10
 extern int approximate;           // -a
 extern int max_queries;           // 200 (src/distributed_image_search.cc:83)
+extern const char* index_out;     // -o: build-tables writes the built index here
+extern const char* index_in;      // -x: search tools read a built index instead of building from binary_file
 extern int query_image_id;        // -I, byid mode (argv[9] of src/distributed_image_search.cc:153)
 
 void configure(int argc, char* argv[]);

@@ -40,6 +40,10 @@ class GpuTableProxy : public BaseProxy<google::protobuf::Message, google::protob
   int load_code_file(const char* path, uint64_t max_codes = 0);
   // uploads what was put() and (re)builds the tables; 0 on success
   int finalize();
+  // persistence: the reference's tables outlive the builder process in the KV servers; here they can be written
+  // to a file by build-tables and read back by the search tools (vc_index_save / vc_index_load)
+  int save(const char* path);
+  int load(const char* path);          // replaces init() + load_codes() + finalize()
 
   vc_index* handle() { return ix_; }
   uint64_t size() const;

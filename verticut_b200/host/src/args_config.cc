@@ -17,6 +17,8 @@ int knn = 10;
 int approximate = 0;
 int max_queries = 200;
 int query_image_id = -1;
+const char* index_out = 0;
+const char* index_in = 0;
 
 static struct option long_options[] = {
     {"server", required_argument, 0, 's'},      {"config_path", required_argument, 0, 'c'},
@@ -37,6 +39,7 @@ void usage() {
   printf("-k : Find k nearest neighbors.\n");
   printf("-a : approximate search (factor 20).\n");
   printf("-I : image id to query by (byid mode).\n");
+  printf("-o : build-tables: write the built index to this file.  -x : search tools: read the index from this file instead of building it from -f.\n");
   printf("-r : The read mode (accepted for compatibility, Pilaf only).\n");
   printf("--help -h : help information.\n");
   exit(-1);
@@ -45,7 +48,7 @@ void usage() {
 void configure(int argc, char* argv[]) {
   int opt, opt_index = 0;
   optind = 1;
-  while ((opt = getopt_long(argc, argv, "c:b:r:n:s:i:k:f:q:I:ah", long_options, &opt_index)) != -1) {
+  while ((opt = getopt_long(argc, argv, "c:b:r:n:s:i:k:f:q:I:o:x:ah", long_options, &opt_index)) != -1) {
     switch (opt) {
       case 'n': n_tables = atoi(optarg); break;
       case 's': server = optarg; break;
@@ -58,6 +61,8 @@ void configure(int argc, char* argv[]) {
       case 'q': query_file = optarg; break;
       case 'a': approximate = 1; break;
       case 'I': query_image_id = atoi(optarg); break;
+      case 'o': index_out = optarg; break;
+      case 'x': index_in = optarg; break;
       default: usage();
     }
   }

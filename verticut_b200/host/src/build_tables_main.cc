@@ -61,6 +61,7 @@ int main(int argc, char* argv[]) {
   vc_index_get_info(proxy.handle(), &info);
   printf("images : %llu, tables : %u x %u-bit, load : %.3f s, build : %.3f s, device bytes : %llu\n",
          (unsigned long long)info.n_codes, info.n_tables, info.substring_bits, t1 - t0, t2 - t1, (unsigned long long)info.device_bytes);
+  if (index_out && proxy.save(index_out) != 0) { fprintf(stderr, "can't write %s: %s\n", index_out, proxy.last_error()); return 1; }
   int rc2 = check ? run_integrity(&proxy) : 0;
   proxy.close();
   return rc2;

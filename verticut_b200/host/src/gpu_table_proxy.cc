@@ -67,6 +67,21 @@ int GpuTableProxy::load_code_file(const char* path, uint64_t max_codes) {
   return 0;
 }
 
+int GpuTableProxy::save(const char* path) {
+  if (finalize() != 0) return -1;
+  return vc_index_save(ix_, path) == VC_OK ? 0 : -1;
+}
+
+int GpuTableProxy::load(const char* path) {
+  if (ix_) { vc_index_destroy(ix_); ix_ = 0; }
+  if (vc_index_load(device_, path, &ix_) != VC_OK) { fprintf(stderr, "GpuTableProxy: %s\n", vc_last_error()); return -1; }
+  vc_index_info info;
+  vc_index_get_info(ix_, &info);
+  bits_ = (int)info.code_bits; tables_ = (int)info.n_tables; first_id_ = info.first_id;
+  dirty_ = false;
+  return 0;
+}
+
 int GpuTableProxy::finalize() {
   if (!ix_) return -1;
   if (!staged_codes_.empty()) {

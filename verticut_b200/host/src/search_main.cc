@@ -38,13 +38,18 @@ int main(int argc, char* argv[]) {
   if (argc < 2) usage();
   const char* mode = argv[1];
   configure(argc - 1, argv + 1);
-  const int rec = binary_bits / 8;
+  int rec = binary_bits / 8;
   const bool linear = !strcmp(mode, "linear");
   GpuTableProxy proxy(binary_bits, linear ? 0 : n_tables);
   double t0 = now();
   if (proxy.init(config_path) != 0) { fprintf(stderr, "proxy init failed: %s\n", proxy.last_error()); return 1; }
-  if (proxy.load_code_file(binary_file, (uint64_t)image_total) != 0) { fprintf(stderr, "Can't open file %s.\n", binary_file); return 1; }
-  if (proxy.finalize() != 0) { fprintf(stderr, "build failed: %s\n", proxy.last_error()); return 1; }
+  if (index_in) {
+    if (proxy.load(index_in) != 0) { fprintf(stderr, "Can't read index %s\n", index_in); return 1; }
+  } else {
+    if (proxy.load_code_file(binary_file, (uint64_t)image_total) != 0) { fprintf(stderr, "Can't open file %s.\n", binary_file); return 1; }
+    if (proxy.finalize() != 0) { fprintf(stderr, "build failed: %s\n", proxy.last_error()); return 1; }
+  }
+  rec = proxy.code_bytes();
   double t_connect = now() - t0;
   if (!strcmp(mode, "integrity")) return run_integrity(&proxy);
   if (!strcmp(mode, "byid")) {
