@@ -874,8 +874,14 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   bool granular = ix->mih_table_steps > 0 && max_radius < 0;
   while (n_active > 0 && r <= sbits) {
     const uint32_t t1 = granular ? t0 + 1 : m;
-    p.radius = r; p.t_begin = t0; p.t_end = t1; p.active = cur; p.n_active = n_active; p.next_active = nxt;
-    const uint64_t total_probes = (uint64_t)n_active * (t1 - t0) * host_binom(sbits, r);
+    // radius 0 alone can only end a search whose k-th distance is below m; in the adaptive rhythm it is probed
+    // together with radius 1 (one step less; its few, long work items overlap with radius 1's many)
+    const uint32_t r_lo = r;
+    if (r == 0 && !granular && ix->mih_table_steps < 0 && sbits >= 1 && max_radius != 0) r = 1;
+    p.radius = r; p.r_lo = r_lo; p.t_begin = t0; p.t_end = t1; p.active = cur; p.n_active = n_active; p.next_active = nxt;
+    uint64_t per_table_probes = 0;
+    for (uint32_t rr = r_lo; rr <= r; ++rr) per_table_probes += host_binom(sbits, rr);
+    const uint64_t total_probes = (uint64_t)n_active * (t1 - t0) * per_table_probes;
     if ((rc = ix->b_qlist.ensure(std::max<uint64_t>(total_probes, 1) * 4))) return rc;
     p.qlist = (uint32_t*)ix->b_qlist.p;
     const int pgrid = grid_for(total_probes, 256, ix->num_sms);

@@ -44,7 +44,8 @@ struct BmihItem { uint32_t t, c0, c1, qbeg, qn; };
 struct BmihParams {
   const uint32_t* queries;      // [nq][2W]
   uint32_t nq, k, m, sbits;
-  uint32_t radius;              // radius of the step being processed
+  uint32_t radius;              // (highest) radius of the step being processed
+  uint32_t r_lo;                // lowest radius of the step: radii [r_lo, radius] are probed together (normally r_lo == radius)
   uint32_t t_begin, t_end;      // ... and its tables [t_begin, t_end): a whole radius (0, m) or one table of it
   uint32_t cpi;                 // codes per work item (multiple of the step size)
   int max_radius;
@@ -78,16 +79,19 @@ struct BmihParams {
 // pass 0: count queries per non-empty bucket (+ statistics); pass 1: write the query into its bucket's list
 template <int W>
 __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
-  const uint32_t per_table = c_binom[p.sbits][p.radius];
+  uint32_t per_table = 0;                                     // probes per table: all masks of weight r_lo .. radius
+  for (uint32_t r = p.r_lo; r <= p.radius; ++r) per_table += c_binom[p.sbits][r];
   const uint64_t per_q = (uint64_t)per_table * (p.t_end - p.t_begin);
   const uint64_t total = per_q * p.n_active;
   for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t a = (uint32_t)(it / per_q);
     const uint32_t rem = (uint32_t)(it % per_q);
-    const uint32_t t = p.t_begin + rem / per_table, pidx = rem % per_table;
+    const uint32_t t = p.t_begin + rem / per_table;
+    uint32_t pidx = rem % per_table, rad = p.r_lo;
+    while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
     const uint32_t q = p.active[a];
     const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
-    const uint32_t key = qkey ^ unrank_mask(p.sbits, p.radius, pidx);
+    const uint32_t key = qkey ^ unrank_mask(p.sbits, rad, pidx);
     const uint32_t* rp = p.tables[t].row_ptr;
     const uint32_t len = rp[key + 1] - rp[key];
     const uint32_t b = (t << p.sbits) + key;
@@ -137,15 +141,17 @@ template <int W>
 __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
                                          CodeRegs<W> c, uint32_t* qrec /* shared: query words, then tau */, uint32_t tau_s) {
   const BmihParams& p = *pp;
-  // first-discoverer test: table t found this code at substring distance exactly `radius`; it is emitted here
-  // only if no other table found it at a smaller distance, or at the same distance with a lower table id
+  // first-discoverer test: table t holds this code at substring distance r_own from the query (the radius at
+  // which this bucket was probed for this query); it is emitted here only if no other table holds it at a
+  // smaller substring distance, or at the same one with a lower table id
   uint32_t x[2 * W];
 #pragma unroll
   for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qrec[i];
+  const uint32_t r_own = __popc(substring<W>(x, t, p.sbits));
   for (uint32_t t2 = 0; t2 < p.m; ++t2) {
     if (t2 == t) continue;
     const uint32_t sd = __popc(substring<W>(x, t2, p.sbits));
-    if (sd < p.radius || (sd == p.radius && t2 < t)) return;
+    if (sd < r_own || (sd == r_own && t2 < t)) return;
   }
   const uint64_t key = pack_key(d, p.tables[t].ids[j]);
   if (key >= __ldcg(&p.gtaukey[qid])) return;
@@ -347,7 +353,8 @@ __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uin
   }
   if (p.max_radius < 0) stop = stop || (tau != kInfDist && tau + 1 <= p.m * r + p.t_end);
   p.gradius[q] = r;
-  p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][r];      // n_sub_reads_ of this step
+  for (uint32_t rr = p.r_lo; rr <= r; ++rr)
+    p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][rr];    // n_sub_reads_ of this step
   if (p.gflag[q] & 1u) *any_overflow = 1;                                                // buffer overflowed: redone by the per-query kernel
   // would this query stop somewhere inside the next radius even if tau did not improve any more?
   if (!stop && level_done && tau != kInfDist && tau + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
