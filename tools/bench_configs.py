@@ -57,7 +57,38 @@ def run(name, n, bits, m, k, nq, max_radius=-1, check=8, scan_batches=(1, 256)):
     return out
 
 
+def scan_sweep(n=1_000_000_000, bits=64, k=100):
+    """Config C4: brute-force scan of 1 B x 64-bit codes, batch sweep 1..4096, against the roofline
+    max(code bytes / HBM peak, tests / POPC peak)."""
+    nbytes = bits // 8
+    ix = capi.Index(bits, 0)
+    ix.add_synthetic(n, 12345)
+    ix.set_param("profile", 1)
+    popc_peak = 15.4 * ix.get_param("num_sms") * 1.965e9
+    rows = []
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+        q = np.random.default_rng(B).integers(0, 256, size=(B, nbytes), dtype=np.uint8)
+        ix.search_linear(q, k)
+        t0 = time.perf_counter()
+        reps = 3 if B <= 64 else 1
+        ks = []
+        for _ in range(reps):
+            ix.search_linear(q, k)
+            ks.append(ix.get_param("last_kernel_ns"))
+        dt = (time.perf_counter() - t0) / reps
+        kern = float(np.mean(ks)) * 1e-9
+        bound = max(n * nbytes / (PEAK * 1e9), B * n / popc_peak)
+        rows.append({"batch": B, "queries_per_s_e2e": B / dt, "scan_kernel_ms": kern * 1e3, "hbm_GBps": n * nbytes / kern / 1e9,
+                     "tests_per_s": B * n / kern, "roofline_ms": bound * 1e3, "frac_of_roofline": bound / kern,
+                     "bound": "hbm" if n * nbytes / (PEAK * 1e9) > B * n / popc_peak else "popc"})
+    ix.close()
+    return {"config": "C4 brute-force scan, 1 B x 64-bit codes, k=100, one GPU, batch sweep", "rows": rows}
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        print(json.dumps(scan_sweep(), indent=1))
+        sys.exit(0)
     res = []
     res.append(run("C1 linear 1M x 64-bit, 1k queries, k=10 (GPU; MIH m=4 beside it)", 1_000_000, 64, 4, 10, 1000, scan_batches=(1000,)))
     res.append(run("C2 MIH 64-bit m=4, 100M codes, k=100", 100_000_000, 64, 4, 100, 4096))

@@ -684,6 +684,11 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   while (total_smem(qt, stages) > ix->smem_optin && stages > 2) --stages;
   while (total_smem(qt, stages) > ix->smem_optin && qt > 1) --qt;
   if (total_smem(qt, stages) > ix->smem_optin) return fail(VC_ERR_ARG, "k = %u needs more shared memory than the device has", k);
+  // equal query tiles: 32 queries with room for 31 per CTA become 16 + 16, not 31 + 1
+  {
+    const uint32_t tiles = (nq + qt - 1) / qt;
+    qt = (nq + tiles - 1) / tiles;
+  }
   p.QT = qt; p.stages = stages;
   p.n_qtiles = (nq + qt - 1) / qt;
   const size_t smem = total_smem(qt, stages);
@@ -882,6 +887,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     uint64_t per_table_probes = 0;
     for (uint32_t rr = r_lo; rr <= r; ++rr) per_table_probes += host_binom(sbits, rr);
     const uint64_t total_probes = (uint64_t)n_active * (t1 - t0) * per_table_probes;
+    if (total_probes >= 0xFFFFFFF0ull) return fail(VC_ERR_ARG, "batch of %u queries needs %llu probes in one step; split the batch", nq, (unsigned long long)total_probes);
     if ((rc = ix->b_qlist.ensure(std::max<uint64_t>(total_probes, 1) * 4))) return rc;
     p.qlist = (uint32_t*)ix->b_qlist.p;
     const int pgrid = grid_for(total_probes, 256, ix->num_sms);
