@@ -1,3 +1,4 @@
+timeout 1200 python -m pytest tests/test_gpu_scan_batched.py tests/test_gpu_linear.py -m gpu -x -q 2>&1 | tail -4
 python tools/bench_configs.py sweep > gpurun_out/scan_sweep.json 2> gpurun_out/scan_sweep.err; tail -3 gpurun_out/scan_sweep.err
 python - <<'PY'
 import json

@@ -8,11 +8,15 @@ from verticut_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
+SCAN_BATCHED = -1     # module switch (test_gpu_scan_batched.py): 1 forces the verify-kernel scan path, 0 the TMA-ring kernel
+
+
 def _run(oracle, n, bits, nq, k, first_id=0, params=None, seed=12345):
     nbytes = bits // 8
     codes = oracle.synth_codes(seed, first_id, n, nbytes)
     queries = oracle.synth_codes(67890, 0, nq, nbytes)
     ix = capi.Index(bits, 0, first_id=first_id)
+    ix.set_param("scan.batched", SCAN_BATCHED)
     for name, v in (params or {}).items():
         ix.set_param(name, v)
     ix.add(codes)
@@ -57,6 +61,7 @@ def test_linear_heavy_ties(oracle):
     codes = np.tile(np.arange(8, dtype=np.uint8), (n, 1))
     queries = oracle.synth_codes(5, 0, 4, 8)
     ix = capi.Index(64, 0)
+    ix.set_param("scan.batched", SCAN_BATCHED)
     ix.add(codes)
     ids, dists, counts = ix.search_linear(queries, k)
     oid, od, oc = oracle.linear_search(codes, queries, k)

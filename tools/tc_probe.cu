@@ -1,0 +1,248 @@
+// tcgen05 probe for the tensor-core formulation of batched Hamming distance (north_star: "tensor cores only if a
+// +-1 int8 tcgen05 GEMM formulation beats the popcount path").  Three measurements on one B200:
+//   1. check   D[128 codes][256 queries] = A * B^T through tcgen05.mma (kind::i8 and kind::f8f6f4) from operands the
+//              threads expand themselves into the no-swizzle K-major canonical shared-memory layout, against the host:
+//              A[c][i] = bit i of code c (0/1), A[c][pad] = 1;  B[q][i] = 1 - 2 * (bit i of query q), B[q][pad] =
+//              popc(q) - tau_q - 1   =>   D[c][q] = hamming(c, q) - tau_q - 1  (negative <=> candidate).
+//   2. ldtm    tcgen05.ld throughput in bytes/clk/SM for 4 / 8 / 16 warps (the epilogue bound of that formulation).
+//   3. mma     clocks per 128 x 256 x 32-byte tcgen05.mma for kind::i8 and kind::f8f6f4.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int KIND>   // 0: i8, 1: f8f6f4
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == 0)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+#define TMEM_LD32(r, taddr)                                                                                                         \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"  \
+               "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                             \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+               : "r"(taddr))
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// LBO = byte distance of core matrices adjacent in K, SBO = of 8-row groups adjacent in M/N
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int kind, int M, int N) {
+  // c_format [4,6): 1 = F32, 2 = S32; a_format [7,10), b_format [10,13): i8: 1 = signed; f8f6f4: 0 = E4M3; K-major both
+  return (kind == 0 ? (2u << 4) | (1u << 7) | (1u << 10) : (1u << 4)) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int M_ = 128, N_ = 256, KB = 96;           // 64 code bits + 32 pad bytes
+constexpr uint32_t LBO = 128, SBO = (KB / 16) * 128;
+
+__device__ __forceinline__ uint32_t op_off(uint32_t row, uint32_t kbyte) {
+  return (kbyte >> 4) * LBO + (row >> 3) * SBO + (row & 7) * 16 + (kbyte & 15);
+}
+
+// ---- 1. correctness ------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) check_kernel(const uint64_t* codes, const uint64_t* queries, const int* pad, int32_t* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                      // 128 x 96
+  uint8_t* sB = smem + M_ * KB;            // 256 x 96
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const uint8_t one = KIND == 0 ? 1 : 0x38, mone = KIND == 0 ? 0xFF : 0xB8;
+  for (uint32_t i = tid; i < (M_ + N_) * KB; i += 128) smem[i] = 0;
+  __syncthreads();
+  {
+    const uint64_t c = codes[tid];
+    for (int b = 0; b < 64; ++b) sA[op_off(tid, b)] = (c >> b) & 1 ? one : 0;
+    sA[op_off(tid, 64)] = one;
+    for (uint32_t q = tid; q < N_; q += 128) {
+      const uint64_t v = queries[q];
+      for (int b = 0; b < 64; ++b) sB[op_off(q, b)] = (v >> b) & 1 ? mone : one;
+      if (KIND == 0) sB[op_off(q, 64)] = (uint8_t)(int8_t)pad[q];
+    }
+  }
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(KIND, M_, N_);
+    for (int k = 0; k < KB / 32; ++k)
+      tc_mma<KIND>(tb, make_desc(smem_u32(sA) + k * 2 * LBO, LBO, SBO), make_desc(smem_u32(sB) + k * 2 * LBO, LBO, SBO), idesc, k > 0);
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N_; c0 += 32) {
+    uint32_t r[32];
+    TMEM_LD32(r, tb + ((warp * 32) << 16) + c0);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(size_t)tid * N_ + c0 + j] = KIND == 0 ? (int32_t)r[j] : (int32_t)__uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 256);
+}
+
+// ---- 2. tcgen05.ld throughput --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) ldtm_kernel(int iters, uint32_t* sink, long long* clk) {
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base + (((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t a[32], b[32], c[32], d[32];
+    const uint32_t col = ((it + warp) & 3) * 128;
+    TMEM_LD32(a, tb + col);
+    TMEM_LD32(b, tb + col + 32);
+    TMEM_LD32(c, tb + col + 64);
+    TMEM_LD32(d, tb + col + 96);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) acc |= (a[j] | a[j + 1]) | (b[j] | b[j + 1]) | ((c[j] | c[j + 1]) | (d[j] | d[j + 1]));
+  }
+  const long long t1 = clock64();
+  if (acc == 0x12345678u) sink[0] = acc;
+  __syncthreads();
+  if (tid == 0) clk[blockIdx.x] = t1 - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- 3. MMA rate ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(128) mma_rate_kernel(int iters, long long* clk) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < (M_ + N_) * KB; i += 128) smem[i] = 0;
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  long long t0 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(KIND, M_, N_);
+    const uint64_t ad = make_desc(smem_u32(smem), LBO, SBO), bd = make_desc(smem_u32(smem + M_ * KB), LBO, SBO);
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) tc_mma<KIND>(tb + (it & 1) * 256, ad, bd, idesc, 1);
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) clk[blockIdx.x] = clock64() - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+static uint64_t sm64(uint64_t& s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+
+template <int KIND>
+static int run_check() {
+  std::vector<uint64_t> codes(M_), queries(N_);
+  std::vector<int> pad(N_);
+  uint64_t s = 42 + KIND;
+  for (auto& c : codes) c = sm64(s);
+  for (int q = 0; q < N_; ++q) { queries[q] = sm64(s); pad[q] = KIND == 0 ? __builtin_popcountll(queries[q]) - (20 + q % 20) - 1 : 0; }
+  uint64_t *dc, *dq; int* dp; int32_t* dout;
+  CK(cudaMalloc(&dc, M_ * 8)); CK(cudaMalloc(&dq, N_ * 8)); CK(cudaMalloc(&dp, N_ * 4)); CK(cudaMalloc(&dout, M_ * N_ * 4));
+  CK(cudaMemcpy(dc, codes.data(), M_ * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dq, queries.data(), N_ * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dp, pad.data(), N_ * 4, cudaMemcpyHostToDevice));
+  const size_t smem = (M_ + N_) * KB;
+  CK(cudaFuncSetAttribute(check_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  check_kernel<KIND><<<1, 128, smem>>>(dc, dq, dp, dout);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> out(M_ * N_);
+  CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int c = 0; c < M_; ++c)
+    for (int q = 0; q < N_; ++q) {
+      const int ham = __builtin_popcountll(codes[c] ^ queries[q]);
+      const int want = KIND == 0 ? ham - (20 + q % 20) - 1 : ham - __builtin_popcountll(queries[q]);
+      if (out[c * N_ + q] != want && bad++ < 5) printf("  mismatch c=%d q=%d got %d want %d\n", c, q, out[c * N_ + q], want);
+    }
+  printf("check kind=%s: %s (%d mismatches of %d)\n", KIND == 0 ? "i8" : "f8f6f4(e4m3)", bad ? "FAIL" : "OK", bad, M_ * N_);
+  return bad;
+}
+
+int main(int argc, char** argv) {
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  int rc = 0;
+  rc |= run_check<0>();
+  rc |= run_check<1>();
+  long long* dclk; uint32_t* dsink;
+  CK(cudaMalloc(&dclk, sms * 8)); CK(cudaMalloc(&dsink, 4));
+  std::vector<long long> clk(sms);
+  for (int threads : {128, 256, 512}) {
+    const int iters = 4000;
+    ldtm_kernel<<<sms, threads>>>(iters, dsink, dclk);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+    const double bytes = (double)iters * (threads / 32) * 4 * 32 * 32 * 4;
+    printf("ldtm %2d warps/SM: %.1f bytes/clk/SM = %.1f 32-bit results/clk/SM\n", threads / 32, bytes / avg, bytes / avg / 4);
+  }
+  const size_t smem = (M_ + N_) * KB;
+  CK(cudaFuncSetAttribute(mma_rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(mma_rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int kind = 0; kind < 2; ++kind) {
+    const int iters = 3000;
+    if (kind == 0) mma_rate_kernel<0><<<sms, 128, smem>>>(iters, dclk); else mma_rate_kernel<1><<<sms, 128, smem>>>(iters, dclk);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+    printf("mma kind=%s 128x256x32B: %.1f clk per instruction = %.0f MAC/clk/SM, %.0f 64-bit code-query tests/clk/SM at 3 instr per tile\n",
+           kind == 0 ? "i8" : "f8f6f4", avg / iters, 128.0 * 256 * 32 / (avg / iters), 128.0 * 256 / (3 * avg / iters));
+  }
+  return rc;
+}

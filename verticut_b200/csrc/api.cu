@@ -108,6 +108,9 @@ struct vc_index {
   int64_t scan_qt = 0;            // 0 auto
   int64_t scan_waves = 0;         // 0 auto
   int64_t scan_stages = 0;        // 0 auto: ring depth
+  int64_t scan_batched = -1;        // large batches through the verify kernel: -1 auto, 0 never, 1 always
+  int64_t scan_batched_min = 8;
+  int64_t last_scan_batched = 0;
   int64_t scan_ctas_per_sm = 2;    // shared-memory plan targets this many resident CTAs per SM
   int64_t scan_interleave = 1;    // slices interleaved step-wise (1) or contiguous (0)
   int64_t scan_smem_kb = 0;       // 0 auto: shared memory budget per CTA for the query tile
@@ -632,6 +635,88 @@ int vc_merge_topk(int device, const uint64_t* lists, uint32_t n_lists, uint32_t 
 // ------------------------------------------------------------------------------------------------
 }  // extern "C"
 
+template <int W, bool PF, int U4>
+static int launch_bmih_verify(const BmihParams& p, int num_sms, cudaStream_t st, int* grid_io) {
+  if (*grid_io == 0) {
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, PF, U4>, kBmihThreads, 0));
+    *grid_io = std::max(1, occ) * num_sms;
+  }
+  bmih_verify_kernel<W, PF, U4><<<*grid_io, kBmihThreads, 0, st>>>(p);
+  return VC_OK;
+}
+
+static int search_linear_ring(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, cudaStream_t st);
+
+// Brute-force scan of a large batch through the batched-MIH verify kernel (bmih.cuh): warp-granular work items of
+// <= 16 K codes x <= 32 queries, launch-wide thresholds, per-query global candidate buffers, one settle pass.
+// Falls back to the TMA-ring kernel if a candidate buffer overflows (heavy ties).
+template <int W>
+static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, cudaStream_t st) {
+  using Cfg = BmihCfg<W>;
+  int rc;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
+               o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
+               o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
+               o_xhist = take((size_t)nq * Cfg::HB * 4), o_ctr = take(128), o_tab = take(sizeof(TableDev));
+  if ((rc = ix->b_state.ensure(off))) return rc;
+  unsigned char* sb = (unsigned char*)ix->b_state.p;
+  uint32_t* ctr = (uint32_t*)(sb + o_ctr);
+  BmihParams p;
+  memset(&p, 0, sizeof p);
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = 1; p.sbits = 0; p.max_radius = 0;
+  p.scan_mode = 1; p.first_id = ix->first_id;
+  TableDev pseudo;
+  memset(&pseudo, 0, sizeof pseudo);
+  pseudo.codes = ix->d_codes;
+  CU(cudaMemcpyAsync(sb + o_tab, &pseudo, sizeof pseudo, cudaMemcpyHostToDevice, st));
+  p.tables = (const TableDev*)(sb + o_tab);
+  p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
+  p.bucket_codes = (unsigned long long*)(ctr + 8); p.pair_count = (unsigned long long*)(ctr + 10);
+  p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
+  p.gtau = (uint32_t*)(sb + o_tau); p.ghist = (uint32_t*)(sb + o_hist); p.gflag = (uint32_t*)(sb + o_flag);
+  p.gradius = (uint32_t*)(sb + o_rad); p.gprobes = (unsigned long long*)(sb + o_probes); p.gcands = (unsigned long long*)(sb + o_cands);
+  uint32_t* ident = (uint32_t*)(sb + o_actA);           // 0 .. nq-1: the query list of every item, and the settle list
+  p.next_active = (uint32_t*)(sb + o_actB);
+  uint32_t* xhist = (uint32_t*)(sb + o_xhist);
+  p.qlist = ident;
+  p.cpi = 8 * Cfg::STEP;
+  const uint64_t n = ix->n;
+  const uint32_t nc = (uint32_t)((n + p.cpi - 1) / p.cpi), nqc = (nq + kBmihQT - 1) / kBmihQT;
+  const uint64_t n_items64 = (uint64_t)nc * nqc;
+  if (n_items64 >= 0xFFFFFFF0ull) return fail(VC_ERR_ARG, "batch too large for one scan call; split it");
+  const uint32_t n_items = (uint32_t)n_items64;
+  if ((rc = ix->b_items.ensure(std::max<size_t>(n_items, 1) * sizeof(BmihItem)))) return rc;
+  p.items = (BmihItem*)ix->b_items.p;
+  CU(cudaMemsetAsync(ctr, 0, 128, st));
+  CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));
+  bmih_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p, ident);
+  scan_bootstrap_kernel<W><<<nq, 256, 0, st>>>(p, ix->d_codes, n);
+  scan_items_kernel<<<grid_for(std::max<uint32_t>(n_items, 1), 256, ix->num_sms), 256, 0, st>>>(p.items, n, p.cpi, nq, nqc, n_items);
+  CU(cudaMemcpyAsync(ctr, &n_items, 4, cudaMemcpyHostToDevice, st));
+  const bool pf = ix->scan_prefilter < 0 ? (W <= 2) : ix->scan_prefilter != 0;
+  int grid = 0;
+  if (ix->profile) cudaEventRecord(ix->ev0, st);
+  rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &grid);
+  if (rc) return rc;
+  if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
+  bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, ident, nq, xhist);
+  bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, nullptr);
+  ix->launches += 6;
+  CU(cudaGetLastError());
+  // any overflow?  (flags are written by the append path; one small read-back)
+  std::vector<uint32_t> flags(nq);
+  CU(cudaMemcpyAsync(flags.data(), p.gflag, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  bool overflow = false;
+  for (uint32_t q = 0; q < nq && !overflow; ++q) overflow = (flags[q] & 1u) != 0;
+  ix->last_scan_batched = overflow ? 0 : 1;
+  if (overflow) return search_linear_ring(ix, d_queries, nq, k, d_out_keys, st);
+  return VC_OK;
+}
+
 template <int W, bool PF>
 static int launch_scan(vc_index* ix, const ScanParams& p, size_t smem, cudaStream_t st) {
   auto kern = scan_topk_kernel<W, PF>;
@@ -659,6 +744,22 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   if (nq == 0) return VC_OK;
   DeviceGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
+  // small batches are HBM-bound: the TMA-ring kernel streams the shard once at ~0.94 of the copy peak; larger
+  // batches are POPC-bound and go through the warp-granular verify kernel
+  // (candidates appended per query ~ 15-20 k before the thresholds settle: automatic only while that fits the buffer)
+  const bool batched = ix->scan_batched > 0 || (ix->scan_batched < 0 && nq >= (uint32_t)ix->scan_batched_min && k <= 128);
+  ix->last_scan_batched = 0;
+  if (batched && k < (uint32_t)kBmihCap / 2 && ix->n > 0 && ix->n < 0xFFFFFFFFull) {
+    if (ix->W == 1) return scan_batched<1>(ix, d_queries, nq, k, d_out_keys, st);
+    if (ix->W == 2) return scan_batched<2>(ix, d_queries, nq, k, d_out_keys, st);
+    return scan_batched<4>(ix, d_queries, nq, k, d_out_keys, st);
+  }
+  return search_linear_ring(ix, d_queries, nq, k, d_out_keys, st);
+}
+
+}  // extern "C"
+
+static int search_linear_ring(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, cudaStream_t st) {
   const uint32_t W = ix->W;
   const int qstride = W == 1 ? ScanCfg<1>::QSTRIDE : W == 2 ? ScanCfg<2>::QSTRIDE : ScanCfg<4>::QSTRIDE;
   const int hb = W == 1 ? ScanCfg<1>::HB : W == 2 ? ScanCfg<2>::HB : ScanCfg<4>::HB;
@@ -750,8 +851,6 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
 // ------------------------------------------------------------------------------------------------
 // MIH
 // ------------------------------------------------------------------------------------------------
-}  // extern "C"
-
 template <int W, bool APPROX>
 static int launch_mih(vc_index* ix, const MihParams& p, cudaStream_t st) {
   auto kern = mih_search_kernel<W, APPROX>;
@@ -764,10 +863,6 @@ static int launch_mih(vc_index* ix, const MihParams& p, cudaStream_t st) {
   CU(cudaGetLastError());
   return VC_OK;
 }
-
-extern "C" {
-
-}  // extern "C"
 
 static int mih_per_query(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
                          uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
@@ -803,17 +898,6 @@ static int scan_inplace_small(vc_index* ix, uint32_t* d, uint64_t n, uint32_t* s
 }
 
 // Bucket-stationary batched MIH (bmih.cuh).  Exact or fixed-radius search over dense tables.
-template <int W, bool PF, int U4>
-static int launch_bmih_verify(const BmihParams& p, int num_sms, cudaStream_t st, int* grid_io) {
-  if (*grid_io == 0) {
-    int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bmih_verify_kernel<W, PF, U4>, kBmihThreads, 0));
-    *grid_io = std::max(1, occ) * num_sms;
-  }
-  bmih_verify_kernel<W, PF, U4><<<*grid_io, kBmihThreads, 0, st>>>(p);
-  return VC_OK;
-}
-
 template <int W>
 static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int max_radius,
                        uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
@@ -1062,6 +1146,8 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "scan.stages")) ix->scan_stages = value;
   else if (!strcmp(name, "scan.interleave")) ix->scan_interleave = value;
   else if (!strcmp(name, "scan.ctas_per_sm")) ix->scan_ctas_per_sm = value;
+  else if (!strcmp(name, "scan.batched")) ix->scan_batched = value;
+  else if (!strcmp(name, "scan.batched_min")) ix->scan_batched_min = value;
   else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
   else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
@@ -1092,6 +1178,7 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "scan.last_slices")) *value = ix->last_scan_slices;
   else if (!strcmp(name, "scan.last_smem")) *value = ix->last_scan_smem;
   else if (!strcmp(name, "scan.last_occ")) *value = ix->last_scan_occ;
+  else if (!strcmp(name, "scan.last_batched")) *value = ix->last_scan_batched;
   else if (!strcmp(name, "scan.last_stages")) *value = ix->last_scan_stages;
   else if (!strcmp(name, "scan.stages")) *value = ix->scan_stages;
   else if (!strcmp(name, "num_sms")) *value = ix->num_sms;

@@ -73,6 +73,9 @@ struct BmihParams {
   unsigned long long* gcands;   // [nq]
   uint32_t* next_active;        // [nq]
   uint32_t* n_next;             // [1]
+  // brute-force scan through the same machinery: one pseudo table (the main code array in id order, ids = first_id +
+  // position), one "bucket" = the whole shard, every query in its list; no de-duplication needed
+  uint32_t scan_mode, first_id;
 };
 
 // ---- 1. probes of one level -------------------------------------------------------------------------------
@@ -144,16 +147,18 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
   // first-discoverer test: table t holds this code at substring distance r_own from the query (the radius at
   // which this bucket was probed for this query); it is emitted here only if no other table holds it at a
   // smaller substring distance, or at the same one with a lower table id
-  uint32_t x[2 * W];
+  if (!p.scan_mode) {
+    uint32_t x[2 * W];
 #pragma unroll
-  for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qrec[i];
-  const uint32_t r_own = __popc(substring<W>(x, t, p.sbits));
-  for (uint32_t t2 = 0; t2 < p.m; ++t2) {
-    if (t2 == t) continue;
-    const uint32_t sd = __popc(substring<W>(x, t2, p.sbits));
-    if (sd < r_own || (sd == r_own && t2 < t)) return;
+    for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qrec[i];
+    const uint32_t r_own = __popc(substring<W>(x, t, p.sbits));
+    for (uint32_t t2 = 0; t2 < p.m; ++t2) {
+      if (t2 == t) continue;
+      const uint32_t sd = __popc(substring<W>(x, t2, p.sbits));
+      if (sd < r_own || (sd == r_own && t2 < t)) return;
+    }
   }
-  const uint64_t key = pack_key(d, p.tables[t].ids[j]);
+  const uint64_t key = pack_key(d, p.scan_mode ? p.first_id + j : p.tables[t].ids[j]);
   if (key >= __ldcg(&p.gtaukey[qid])) return;
   const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
   if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
@@ -420,6 +425,69 @@ __global__ void __launch_bounds__(256) bmih_bootstrap_kernel(const BmihParams p)
       if (cum >= p.k) { p.gtau[q] = d; break; }
     }
   }
+}
+
+// ---- brute-force scan through the verify kernel ---------------------------------------------------------------
+// work items: code chunk c x query chunk qc, query chunk fastest (neighbouring items share their codes in L2)
+__global__ void scan_items_kernel(BmihItem* items, uint64_t n, uint32_t cpi, uint32_t nq, uint32_t nqc, uint32_t n_items) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x) {
+    const uint32_t c = i / nqc, qc = i % nqc;
+    BmihItem it;
+    it.t = 0;
+    it.c0 = c * cpi;
+    it.c1 = (uint32_t)min(n, (uint64_t)it.c0 + cpi);
+    const uint32_t qlo = (uint32_t)(((uint64_t)nq * qc) / nqc), qhi = (uint32_t)(((uint64_t)nq * (qc + 1)) / nqc);
+    it.qbeg = qlo; it.qn = qhi - qlo;
+    items[i] = it;
+  }
+}
+// threshold bootstrap for the scan: k-th smallest distance among the first `sample` codes of the shard, one CTA per
+// query.  All warps of the persistent grid start on the same few query chunks, so the first thresholds must already
+// be tight enough for (codes in flight) x (pass rate) to stay far below the candidate buffer: a pilot pass over the
+// first kBmihSample codes bounds the distance, the second pass histograms only what lies below that bound.
+constexpr uint32_t kScanSample = 1u << 18;
+template <int W>
+__global__ void __launch_bounds__(256) scan_bootstrap_kernel(const BmihParams p, const uint64_t* codes, uint64_t n) {
+  constexpr int HB = BmihCfg<W>::HB;
+  __shared__ uint32_t s_hist[HB];
+  __shared__ uint32_t s_bound;
+  const uint32_t tid = threadIdx.x, q = blockIdx.x;
+  uint32_t qw[2 * W];
+#pragma unroll
+  for (int i = 0; i < 2 * W; ++i) qw[i] = p.queries[(size_t)q * 2 * W + i];
+  const uint32_t sample = (uint32_t)min(n, (uint64_t)max(kScanSample, 64u * p.k));
+  const uint32_t pilot = min(sample, max(kBmihSample, 16u * p.k));
+  uint32_t bound = 64 * W;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (uint32_t i = tid; i < HB; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t j1 = pass ? sample : pilot;      // the second pass counts the pilot's codes again: >= k below the bound
+    for (uint32_t j = tid; j < j1; j += 256) {
+      uint32_t d = 0;
+#pragma unroll
+      for (int i = 0; i < W; ++i) {
+        const uint64_t c = codes[(size_t)j * W + i];
+        d += __popc((uint32_t)c ^ qw[2 * i]) + __popc((uint32_t)(c >> 32) ^ qw[2 * i + 1]);
+      }
+      if (d <= bound) atomicAdd(&s_hist[d], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t cum = 0, b = kInfDist;
+      for (uint32_t d = 0; d <= 64 * W; ++d) {
+        cum += s_hist[d];
+        if (cum >= p.k) { b = d; break; }
+      }
+      s_bound = b;
+    }
+    __syncthreads();
+    if (pass == 0) {
+      if (s_bound == kInfDist || pilot == sample) break;
+      bound = s_bound;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && s_bound != kInfDist) p.gtau[q] = s_bound;
 }
 
 __global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_query_stats* stats) {
