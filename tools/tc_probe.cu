@@ -55,6 +55,14 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
                : "r"(taddr))
+#define TMEM_LD32_PACK(r, taddr)                                                                                                    \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"  \
+               "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                                                             \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+               : "r"(taddr))
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, no swizzle, K-major: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
@@ -122,7 +130,70 @@ __global__ void __launch_bounds__(128) check_kernel(const uint64_t* codes, const
   if (warp == 0) tmem_dealloc(tb, 256);
 }
 
+// ---- 1b. f16 accumulators: how are they laid out in TMEM? ------------------------------------------------------------
+__global__ void __launch_bounds__(128) f16_layout_kernel(const uint64_t* codes, const uint64_t* queries, uint32_t* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + M_ * KB;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < (M_ + N_) * KB; i += 128) smem[i] = 0;
+  __syncthreads();
+  const uint64_t c = codes[tid];
+  for (int b = 0; b < 64; ++b) sA[op_off(tid, b)] = (c >> b) & 1 ? 0x38 : 0;
+  for (uint32_t q = tid; q < N_; q += 128) {
+    const uint64_t v = queries[q];
+    for (int b = 0; b < 64; ++b) sB[op_off(q, b)] = (v >> b) & 1 ? 0xB8 : 0x38;
+  }
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  {  // poison the columns first so that untouched cells are recognisable
+    uint32_t r[32];
+    for (int j = 0; j < 32; ++j) r[j] = 0xDEADBEEFu;
+    for (int c0 = 0; c0 < 256; c0 += 32)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+                   "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(tb + ((warp * 32) << 16) + c0), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                   "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]),
+                   "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+                   "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = (0u << 4) | ((uint32_t)(N_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);      // f8f6f4, E4M3 x E4M3, D = F16
+    for (int k = 0; k < 2; ++k)
+      tc_mma<1>(tb, make_desc(smem_u32(sA) + k * 2 * LBO, LBO, SBO), make_desc(smem_u32(sB) + k * 2 * LBO, LBO, SBO), idesc, k > 0);
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N_; c0 += 32) {
+    uint32_t r[32];
+    TMEM_LD32(r, tb + ((warp * 32) << 16) + c0);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(size_t)tid * N_ + c0 + j] = r[j];
+  }
+  {
+    uint32_t r[32];
+    TMEM_LD32_PACK(r, tb + ((warp * 32) << 16));
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(size_t)M_ * N_ + tid * 32 + j] = r[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 256);
+}
+
 // ---- 2. tcgen05.ld throughput --------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(512) ldtm_kernel(int iters, uint32_t* sink, long long* clk) {
   __shared__ uint32_t tmem_base;
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
@@ -135,6 +206,18 @@ __global__ void __launch_bounds__(512) ldtm_kernel(int iters, uint32_t* sink, lo
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
+    if (MODE == 2) {
+      uint32_t a[32], b[32];
+      const uint32_t col = ((it + warp) & 3) * 128;
+      TMEM_LD32_PACK(a, tb + col);
+      TMEM_LD32_PACK(b, tb + col + 64);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) acc = __vimax3_s16x2(acc, a[j], a[j + 1]);
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) acc = __vimax3_s16x2(acc, b[j], b[j + 1]);
+      continue;
+    }
     uint32_t a[32], b[32], c[32], d[32];
     const uint32_t col = ((it + warp) & 3) * 128;
     TMEM_LD32(a, tb + col);
@@ -142,8 +225,12 @@ __global__ void __launch_bounds__(512) ldtm_kernel(int iters, uint32_t* sink, lo
     TMEM_LD32(c, tb + col + 64);
     TMEM_LD32(d, tb + col + 96);
     tmem_ld_wait();
+    if (MODE == 0) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) acc |= (a[j] | a[j + 1]) | (b[j] | b[j + 1]) | ((c[j] | c[j + 1]) | (d[j] | d[j + 1]));
+      for (int j = 0; j < 32; j += 2) acc |= (a[j] | a[j + 1]) | (b[j] | b[j + 1]) | ((c[j] | c[j + 1]) | (d[j] | d[j + 1]));
+    } else {
+      acc |= a[0] | b[1] | c[2] | d[3];
+    }
   }
   const long long t1 = clock64();
   if (acc == 0x12345678u) sink[0] = acc;
@@ -225,12 +312,55 @@ int main(int argc, char** argv) {
   std::vector<long long> clk(sms);
   for (int threads : {128, 256, 512}) {
     const int iters = 4000;
-    ldtm_kernel<<<sms, threads>>>(iters, dsink, dclk);
+    for (int mode = 0; mode < 3; ++mode) {
+      if (mode == 0) ldtm_kernel<0><<<sms, threads>>>(iters, dsink, dclk); else if (mode == 1) ldtm_kernel<1><<<sms, threads>>>(iters, dsink, dclk); else ldtm_kernel<2><<<sms, threads>>>(iters, dsink, dclk);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+      double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+      const double bytes = (double)iters * (threads / 32) * 4 * 32 * 32 * 4;
+      printf("ldtm %2d warps/SM %s: %.1f bytes/clk/SM = %.1f 32-bit results/clk/SM\n", threads / 32, mode == 1 ? "loads only      " : mode == 2 ? "pack::16b (128 columns) + 0.25 VIMNMX3.S16x2/result: 16-bit results counted as 4 bytes" : "loads + 0.5 LOP3/result",
+             bytes / avg, bytes / avg / 4);
+    }
+  }
+  {
+    // f16 accumulator layout
+    std::vector<uint64_t> codes(M_), queries(N_);
+    uint64_t s = 7;
+    for (auto& c : codes) c = sm64(s);
+    for (auto& q : queries) q = sm64(s);
+    uint64_t *dc, *dq; uint32_t* dout;
+    CK(cudaMalloc(&dc, M_ * 8)); CK(cudaMalloc(&dq, N_ * 8)); CK(cudaMalloc(&dout, M_ * (N_ + 32) * 4));
+    CK(cudaMemcpy(dc, codes.data(), M_ * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dq, queries.data(), N_ * 8, cudaMemcpyHostToDevice));
+    const size_t smem2 = (M_ + N_) * KB;
+    CK(cudaFuncSetAttribute(f16_layout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    f16_layout_kernel<<<1, 128, smem2>>>(dc, dq, dout);
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
-    double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
-    const double bytes = (double)iters * (threads / 32) * 4 * 32 * 32 * 4;
-    printf("ldtm %2d warps/SM: %.1f bytes/clk/SM = %.1f 32-bit results/clk/SM\n", threads / 32, bytes / avg, bytes / avg / 4);
+    std::vector<uint32_t> out(M_ * (N_ + 32));
+    CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+    auto h2f = [](uint16_t h) { int e = (h >> 10) & 31, m = h & 1023; float v = e ? ldexpf(1.0f + m / 1024.0f, e - 15) : ldexpf(m / 1024.0f, -14); return (h & 0x8000) ? -v : v; };
+    int packed_ok = 0, unpacked_ok = 0, poison = 0;
+    for (int c = 0; c < M_; ++c)
+      for (int q = 0; q < N_; ++q) {
+        const float want = (float)(__builtin_popcountll(codes[c] ^ queries[q]) - __builtin_popcountll(queries[q]));
+        const uint32_t wp = out[c * N_ + q / 2];
+        if (h2f((uint16_t)(q & 1 ? wp >> 16 : wp & 0xFFFF)) == want) ++packed_ok;
+        if (h2f((uint16_t)(out[c * N_ + q] & 0xFFFF)) == want) ++unpacked_ok;
+      }
+    for (int c = 0; c < M_; ++c) for (int j = 0; j < N_; ++j) poison += out[c * N_ + j] == 0xDEADBEEFu;
+    {
+      // .x32.pack::16b: register j = columns (2j, 2j+1) [64 columns], or something else?
+      int ok64 = 0, ok32 = 0;
+      for (int c = 0; c < M_; ++c)
+        for (int j = 0; j < 32; ++j) {
+          const uint32_t v = out[M_ * N_ + c * 32 + j];
+          const uint32_t lo2 = out[c * N_ + 2 * j] & 0xFFFF, hi2 = out[c * N_ + 2 * j + 1] & 0xFFFF;
+          ok64 += v == (lo2 | (hi2 << 16));
+          if (j < 16) ok32 += v == (lo2 | (hi2 << 16));
+        }
+      printf("pack::16b .x32: registers j = columns (2j | 2j+1 << 16) for %d / %d (first 16 registers: %d / %d)\n", ok64, M_ * 32, ok32, M_ * 16);
+    }
+    printf("f16 accumulators: packed-hypothesis matches %d / %d, unpacked-hypothesis %d / %d, untouched cells %d; row0 cols0-3: %08x %08x %08x %08x col128: %08x\n",
+           packed_ok, M_ * N_, unpacked_ok, M_ * N_, poison, out[0], out[1], out[2], out[3], out[128]);
   }
   const size_t smem = (M_ + N_) * KB;
   CK(cudaFuncSetAttribute(mma_rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
