@@ -8,6 +8,7 @@ from verticut_b200 import capi
 pytestmark = pytest.mark.gpu
 
 
+EXTRA_PARAMS = {}      # module switch (test_gpu_tc.py): knobs for every index built here
 SCAN_BATCHED = -1     # module switch (test_gpu_scan_batched.py): 1 forces the verify-kernel scan path, 0 the TMA-ring kernel
 
 
@@ -17,7 +18,7 @@ def _run(oracle, n, bits, nq, k, first_id=0, params=None, seed=12345):
     queries = oracle.synth_codes(67890, 0, nq, nbytes)
     ix = capi.Index(bits, 0, first_id=first_id)
     ix.set_param("scan.batched", SCAN_BATCHED)
-    for name, v in (params or {}).items():
+    for name, v in {**EXTRA_PARAMS, **(params or {})}.items():
         ix.set_param(name, v)
     ix.add(codes)
     ids, dists, counts = ix.search_linear(queries, k)

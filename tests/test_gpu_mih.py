@@ -10,6 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 BATCHED = 0      # module switch: 1 forces the bucket-stationary batched path wherever it is legal (test_gpu_bmih.py)
+EXTRA_PARAMS = {}   # module switch: further knobs for every index built here (test_gpu_tc.py forces the tensor-core verify kernel)
 
 
 def _mk(oracle, n, bits, m, first_id=0, seed=12345):
@@ -17,6 +18,8 @@ def _mk(oracle, n, bits, m, first_id=0, seed=12345):
     codes = oracle.synth_codes(seed, first_id, n, nbytes)
     ix = capi.Index(bits, m, first_id=first_id)
     ix.set_param("mih.batched", BATCHED)
+    for name, v in EXTRA_PARAMS.items():
+        ix.set_param(name, v)
     ix.add(codes)
     ix.build()
     return codes, ix
@@ -131,6 +134,8 @@ def test_mih_heavy_ties(oracle):
     codes = np.repeat(base, n // 4, axis=0)                # four distinct codes, 1250 copies each
     ix = capi.Index(64, 4)
     ix.set_param("mih.batched", BATCHED)
+    for name, v in EXTRA_PARAMS.items():
+        ix.set_param(name, v)
     ix.add(codes)
     ix.build()
     queries = oracle.synth_codes(67890, 0, 6, 8)

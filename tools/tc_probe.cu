@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t op_off(uint32_t row, uint32_t kbyte) {
   return (kbyte >> 4) * LBO + (row >> 3) * SBO + (row & 7) * 16 + (kbyte & 15);
 }
 
+static uint64_t sm64(uint64_t& s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
 // ---- 1. correctness ------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(128) check_kernel(const uint64_t* codes, const uint64_t* queries, const int* pad, int32_t* out) {
@@ -128,6 +129,123 @@ __global__ void __launch_bounds__(128) check_kernel(const uint64_t* codes, const
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tb, 256);
+}
+
+
+// ---- 1c. the production encoding: codes as A, bytes +-a_j from two instructions per 4 bits (LOP3 + IMAD); queries as B,
+// bytes +-64/a_j; D = 64 * (64 - 2 * hamming); epilogue: packed 16-bit loads + VIMNMX3 row maximum ----------------------
+__device__ __forceinline__ void expand_code_word(uint32_t x, uint32_t* out8) {
+  // out8[j] holds bits j, j+8, j+16, j+24 of x as bytes +a_j (bit clear) / -a_j (bit set); a = 1,1,2,4,8,16,32,64
+  out8[0] = (x & 0x01010101u) * 254u + 0x01010101u;
+  out8[1] = (x & 0x02020202u) * 127u + 0x01010101u;
+  out8[2] = (x & 0x04040404u) * 63u + 0x02020202u;
+  out8[3] = (x & 0x08080808u) * 31u + 0x04040404u;
+  out8[4] = (x & 0x10101010u) * 15u + 0x08080808u;
+  out8[5] = (x & 0x20202020u) * 7u + 0x10101010u;
+  out8[6] = (x & 0x40404040u) * 3u + 0x20202020u;
+  out8[7] = (x & 0x80808080u) * 1u + 0x40404040u;
+}
+__device__ __forceinline__ void expand_query_word(uint32_t x, uint32_t* out8) {
+  const int bw[8] = {64, 64, 32, 16, 8, 4, 2, 1};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = (x >> (j + 8 * i)) & 1 ? -bw[j] : bw[j];
+      r |= (uint32_t)(uint8_t)(int8_t)v << (8 * i);
+    }
+    out8[j] = r;
+  }
+}
+constexpr int KB2 = 64;
+constexpr uint32_t SBO2 = (KB2 / 16) * 128;
+__global__ void __launch_bounds__(128) check2_kernel(const uint64_t* codes, const uint64_t* queries, int n_cols, int32_t* out, int32_t* rowmax) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                      // 128 x 64
+  uint8_t* sB = smem + M_ * KB2;           // n_cols x 64
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  {
+    const uint64_t c = codes[tid];
+    uint32_t o[16];
+    expand_code_word((uint32_t)c, o); expand_code_word((uint32_t)(c >> 32), o + 8);
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sA + g * LBO + (tid >> 3) * SBO2 + (tid & 7) * 16) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    for (uint32_t q = tid; q < (uint32_t)n_cols; q += 128) {
+      const uint64_t v = queries[q];
+      expand_query_word((uint32_t)v, o); expand_query_word((uint32_t)(v >> 32), o + 8);
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(sB + g * LBO + (q >> 3) * SBO2 + (q & 7) * 16) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    }
+  }
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(0, M_, n_cols);
+    for (int k = 0; k < KB2 / 32; ++k)
+      tc_mma<0>(tb, make_desc(smem_u32(sA) + k * 2 * LBO, LBO, SBO2), make_desc(smem_u32(sB) + k * 2 * LBO, LBO, SBO2), idesc, k > 0);
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < n_cols; c0 += 16) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(tb + ((warp * 32) << 16) + c0));
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[(size_t)tid * 256 + c0 + j] = (int32_t)r[j];
+  }
+  // packed row maximum over all columns, 16 columns (8 registers) at a time
+  uint32_t acc = 0x80008000u;
+  for (int c0 = 0; c0 < n_cols; c0 += 16) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(tb + ((warp * 32) << 16) + c0));
+    tmem_ld_wait();
+    for (int j = 0; j < 8; j += 2) acc = __vimax3_s16x2(acc, r[j], r[j + 1]);
+  }
+  rowmax[tid] = max((int32_t)(int16_t)(acc & 0xFFFF), (int32_t)(int16_t)(acc >> 16));
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 256);
+}
+static int run_check2(int n_cols) {
+  std::vector<uint64_t> codes(M_), queries(256);
+  uint64_t s = 4242 + n_cols;
+  for (auto& c : codes) c = sm64(s);
+  for (auto& q : queries) q = sm64(s);
+  for (int i = 0; i < 8; ++i) queries[i] = codes[5 * i] ^ (0x8000000000000001ull << i);      // a few near neighbours
+  uint64_t *dc, *dq; int32_t *dout, *drm;
+  CK(cudaMalloc(&dc, M_ * 8)); CK(cudaMalloc(&dq, 256 * 8)); CK(cudaMalloc(&dout, M_ * 256 * 4)); CK(cudaMalloc(&drm, M_ * 4));
+  CK(cudaMemcpy(dc, codes.data(), M_ * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dq, queries.data(), 256 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0, M_ * 256 * 4));
+  const size_t smem = (M_ + 256) * KB2;
+  CK(cudaFuncSetAttribute(check2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  check2_kernel<<<1, 128, smem>>>(dc, dq, n_cols, dout, drm);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> out(M_ * 256), rm(M_);
+  CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(rm.data(), drm, rm.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0, badmax = 0;
+  for (int c = 0; c < M_; ++c) {
+    int best = -100000;
+    for (int q = 0; q < n_cols; ++q) {
+      const int want = 64 * (64 - 2 * __builtin_popcountll(codes[c] ^ queries[q]));
+      best = want > best ? want : best;
+      if (out[c * 256 + q] != want && bad++ < 5) printf("  check2 mismatch c=%d q=%d got %d want %d\n", c, q, out[c * 256 + q], want);
+    }
+    if (rm[c] != best && badmax++ < 5) printf("  check2 rowmax mismatch c=%d got %d want %d\n", c, rm[c], best);
+  }
+  printf("check2 weighted encoding N=%d: %s (%d value mismatches, %d row-max mismatches)\n", n_cols, bad || badmax ? "FAIL" : "OK", bad, badmax);
+  return bad + badmax;
 }
 
 // ---- 1b. f16 accumulators: how are they laid out in TMEM? ------------------------------------------------------------
@@ -243,7 +361,7 @@ __global__ void __launch_bounds__(512) ldtm_kernel(int iters, uint32_t* sink, lo
 
 // ---- 3. MMA rate ---------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(128) mma_rate_kernel(int iters, long long* clk) {
+__global__ void __launch_bounds__(128) mma_rate_kernel(int iters, long long* clk, int n_cols = N_, int n_acc = 2, int acc_stride = 256) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -258,10 +376,12 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int iters, long long* clk
   const uint32_t tb = tmem_base;
   long long t0 = 0;
   if (tid == 0) {
-    const uint32_t idesc = make_idesc(KIND, M_, N_);
+    const uint32_t idesc = make_idesc(KIND, M_, n_cols);
     const uint64_t ad = make_desc(smem_u32(smem), LBO, SBO), bd = make_desc(smem_u32(smem + M_ * KB), LBO, SBO);
     t0 = clock64();
-    for (int it = 0; it < iters; ++it) tc_mma<KIND>(tb + (it & 1) * 256, ad, bd, idesc, 1);
+    if (n_acc == 1) { for (int it = 0; it < iters; it += 4) { tc_mma<KIND>(tb, ad, bd, idesc, 1); tc_mma<KIND>(tb, ad, bd, idesc, 1); tc_mma<KIND>(tb, ad, bd, idesc, 1); tc_mma<KIND>(tb, ad, bd, idesc, 1); } }
+    else if (n_acc == 2) { for (int it = 0; it < iters; it += 4) { tc_mma<KIND>(tb, ad, bd, idesc, 1); tc_mma<KIND>(tb + acc_stride, ad, bd, idesc, 1); tc_mma<KIND>(tb, ad, bd, idesc, 1); tc_mma<KIND>(tb + acc_stride, ad, bd, idesc, 1); } }
+    else { for (int it = 0; it < iters; it += 4) { tc_mma<KIND>(tb, ad, bd, idesc, 1); tc_mma<KIND>(tb + acc_stride, ad, bd, idesc, 1); tc_mma<KIND>(tb + 2 * acc_stride, ad, bd, idesc, 1); tc_mma<KIND>(tb + 3 * acc_stride, ad, bd, idesc, 1); } }
     tc_commit(&bar);
   }
   mbar_wait(&bar, 0);
@@ -271,7 +391,6 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int iters, long long* clk
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
-static uint64_t sm64(uint64_t& s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
 
 template <int KIND>
 static int run_check() {
@@ -307,6 +426,7 @@ int main(int argc, char** argv) {
   int rc = 0;
   rc |= run_check<0>();
   rc |= run_check<1>();
+  for (int n : {16, 48, 64, 256}) rc |= run_check2(n);
   long long* dclk; uint32_t* dsink;
   CK(cudaMalloc(&dclk, sms * 8)); CK(cudaMalloc(&dsink, 4));
   std::vector<long long> clk(sms);
@@ -373,6 +493,16 @@ int main(int argc, char** argv) {
     double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
     printf("mma kind=%s 128x256x32B: %.1f clk per instruction = %.0f MAC/clk/SM, %.0f 64-bit code-query tests/clk/SM at 3 instr per tile\n",
            kind == 0 ? "i8" : "f8f6f4", avg / iters, 128.0 * 256 * 32 / (avg / iters), 128.0 * 256 / (3 * avg / iters));
+  }
+  for (int n : {16, 32, 64, 128}) {
+    const int iters = 3000;
+    for (int n_acc : {1, 2, 4}) {
+      mma_rate_kernel<0><<<sms, 128, smem>>>(iters, dclk, n, n_acc, 128);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+      double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+      printf("mma kind=i8 128x%dx32B, %d accumulators round-robin: %.1f clk per instruction\n", n, n_acc, avg / iters);
+    }
   }
   return rc;
 }

@@ -16,6 +16,7 @@
 #include "mih.cuh"
 #include "scan.cuh"
 #include "bmih.cuh"
+#include "tcverify.cuh"
 
 using namespace vc;
 
@@ -120,6 +121,9 @@ struct vc_index {
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
+  // tensor-core verify kernel (tcverify.cuh): -1 auto, 0 never, 1 whenever legal
+  int64_t scan_tc = -1, scan_tc_min = 48, last_scan_tc = 0;
+  int64_t mih_tc = -1, mih_tc_ratio = 10, last_mih_tc_steps = 0;
   vc_allreduce_fn allreduce_fn = nullptr;
   void* allreduce_user = nullptr;
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
@@ -646,6 +650,24 @@ static int launch_bmih_verify(const BmihParams& p, int num_sms, cudaStream_t st,
   return VC_OK;
 }
 
+// tensor-core verify kernel: one persistent CTA per SM
+template <int W, int QT>
+static int launch_bmih_verify_tc(const BmihParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = TcCfg<W, QT>;
+  CU(cudaFuncSetAttribute(bmih_verify_tc_kernel<W, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  bmih_verify_tc_kernel<W, QT><<<num_sms, kTcThreads, Cfg::SMEM, st>>>(p);
+  return VC_OK;
+}
+template <int W>
+static int launch_bmih_verify_tc_any(const BmihParams& p, int num_sms, cudaStream_t st) {
+  if constexpr (W == 4) {
+    return p.qt > 64 ? launch_bmih_verify_tc<4, 128>(p, num_sms, st) : launch_bmih_verify_tc<4, 64>(p, num_sms, st);
+  } else {
+    return p.qt > 64 ? launch_bmih_verify_tc<W, 256>(p, num_sms, st) : launch_bmih_verify_tc<W, 64>(p, num_sms, st);
+  }
+}
+template <int W> constexpr uint32_t tc_max_qt() { return W == 4 ? 128u : 256u; }
+
 static int search_linear_ring(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, cudaStream_t st);
 
 // Brute-force scan of a large batch through the batched-MIH verify kernel (bmih.cuh): warp-granular work items of
@@ -682,9 +704,13 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   p.next_active = (uint32_t*)(sb + o_actB);
   uint32_t* xhist = (uint32_t*)(sb + o_xhist);
   p.qlist = ident;
-  p.cpi = 8 * Cfg::STEP;
+  // >= scan.tc_min queries per code: the distance filter goes to the tensor cores (tcverify.cuh)
+  const bool use_tc = ix->scan_tc > 0 || (ix->scan_tc < 0 && nq >= (uint32_t)ix->scan_tc_min);
+  p.cpi = use_tc ? kTcCpi : 8 * Cfg::STEP;
+  p.qt = use_tc ? tc_max_qt<W>() : (uint32_t)kBmihQT;
+  ix->last_scan_tc = use_tc ? 1 : 0;
   const uint64_t n = ix->n;
-  const uint32_t nc = (uint32_t)((n + p.cpi - 1) / p.cpi), nqc = (nq + kBmihQT - 1) / kBmihQT;
+  const uint32_t nc = (uint32_t)((n + p.cpi - 1) / p.cpi), nqc = (nq + p.qt - 1) / p.qt;
   const uint64_t n_items64 = (uint64_t)nc * nqc;
   if (n_items64 >= 0xFFFFFFF0ull) return fail(VC_ERR_ARG, "batch too large for one scan call; split it");
   const uint32_t n_items = (uint32_t)n_items64;
@@ -699,7 +725,8 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   const bool pf = ix->scan_prefilter < 0 ? (W <= 2) : ix->scan_prefilter != 0;
   int grid = 0;
   if (ix->profile) cudaEventRecord(ix->ev0, st);
-  rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &grid);
+  if (use_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
+  else rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &grid);
   if (rc) return rc;
   if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
   bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, ident, nq, xhist);
@@ -932,6 +959,11 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
   p.bucket_codes = (unsigned long long*)(ctr + 8);
   p.pair_count = (unsigned long long*)(ctr + 10);
+  p.scan_mode = 0; p.first_id = ix->first_id;
+  const uint32_t popc_cpi = p.cpi;
+  const bool tc_possible = ix->mih_tc != 0;
+  p.qt = kBmihQT; p.cpi_alt = kTcCpi; p.qt_alt = 64; p.n_items_alt = tc_possible ? ctr + 5 : nullptr;
+  ix->last_mih_tc_steps = 0;
   unsigned long long prev_codes = 0, prev_pairs = 0;
   ix->step_codes.clear(); ix->step_pairs.clear();
   p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
@@ -983,11 +1015,41 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     CU(cudaMemsetAsync(p.bcount, 0, (size_t)n_buckets * 4, st));
     bmih_probe_kernel<W><<<pgrid, 256, 0, st>>>(p, 1);
     CU(cudaMemsetAsync(ctr, 0, 12, st));
+    CU(cudaMemsetAsync(ctr + 5, 0, 4, st));
     const int igrid = grid_for(n_buckets, 256, ix->num_sms);
+    p.cpi = popc_cpi; p.qt = kBmihQT;
     bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 0);
-    CU(cudaMemcpyAsync(h_ctr, ctr, 16, cudaMemcpyDeviceToHost, st));
+    uint32_t h12[12];
+    CU(cudaMemcpyAsync(h12, ctr, 48, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    const uint32_t n_items = h_ctr[0];
+    memcpy(h_ctr, h12, 16);
+    uint32_t n_items = h_ctr[0];
+    // which verify kernel?  pairs / codes = queries per code of this step: the POPC kernel pays for every pair, the
+    // tensor-core kernel a flat >= 91 clocks per 128 codes for up to 64 queries
+    bool step_tc = false;
+    if (tc_possible) {
+      unsigned long long cc, pp;
+      memcpy(&cc, h12 + 8, 8); memcpy(&pp, h12 + 10, 8);
+      const double codes_now = (double)(cc - prev_codes), pairs_now = (double)(pp - prev_pairs);
+      step_tc = ix->mih_tc > 0 || (codes_now > 0 && pairs_now >= (double)ix->mih_tc_ratio * codes_now);
+      if (step_tc) {
+        p.cpi = kTcCpi;
+        if (pairs_now >= 40.0 * codes_now && tc_max_qt<W>() > 64) {
+          // long query lists: 256 (128) queries per item; the item count for that geometry needs its own counting pass
+          p.qt = tc_max_qt<W>(); p.qt_alt = p.qt;
+          CU(cudaMemsetAsync(ctr + 5, 0, 4, st));
+          unsigned long long* keep_bc = p.bucket_codes; uint32_t* keep_n = p.n_items;
+          p.bucket_codes = (unsigned long long*)(ctr + 6); p.n_items = ctr + 4;      // scratch: [4] is cleared before pass 1, [6..7] unused
+          bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 0);
+          p.bucket_codes = keep_bc; p.n_items = keep_n; p.qt_alt = 64;
+          CU(cudaMemcpyAsync(h12, ctr, 48, cudaMemcpyDeviceToHost, st));
+          CU(cudaStreamSynchronize(st));
+          ix->launches++;
+        } else p.qt = 64;
+        n_items = h12[5];
+        ++ix->last_mih_tc_steps;
+      }
+    }
     if ((rc = ix->b_items.ensure(std::max<size_t>(n_items, 1) * sizeof(BmihItem)))) return rc;
     p.items = (BmihItem*)ix->b_items.p;
     CU(cudaMemsetAsync(ctr, 0, 12, st));
@@ -998,7 +1060,8 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       if (!ix->lev[2 * levels]) { CU(cudaEventCreate(&ix->lev[2 * levels])); CU(cudaEventCreate(&ix->lev[2 * levels + 1])); }
       cudaEventRecord(ix->lev[2 * levels], st);
     }
-    if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
+    if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
+    else if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
     else rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &verify_grid);
     if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
@@ -1150,6 +1213,10 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "scan.batched_min")) ix->scan_batched_min = value;
   else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
   else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
+  else if (!strcmp(name, "scan.tc")) ix->scan_tc = value;
+  else if (!strcmp(name, "scan.tc_min")) ix->scan_tc_min = value;
+  else if (!strcmp(name, "mih.tc")) ix->mih_tc = value;
+  else if (!strcmp(name, "mih.tc_ratio")) ix->mih_tc_ratio = value;
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
   else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
@@ -1182,6 +1249,11 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "scan.last_stages")) *value = ix->last_scan_stages;
   else if (!strcmp(name, "scan.stages")) *value = ix->scan_stages;
   else if (!strcmp(name, "num_sms")) *value = ix->num_sms;
+  else if (!strcmp(name, "scan.tc")) *value = ix->scan_tc;
+  else if (!strcmp(name, "scan.last_tc")) *value = ix->last_scan_tc;
+  else if (!strcmp(name, "mih.tc")) *value = ix->mih_tc;
+  else if (!strcmp(name, "mih.tc_ratio")) *value = ix->mih_tc_ratio;
+  else if (!strcmp(name, "mih.last_tc_steps")) *value = ix->last_mih_tc_steps;
   else if (!strcmp(name, "mih.batched")) *value = ix->mih_batched;
   else if (!strcmp(name, "mih.last_batched")) *value = ix->last_mih_batched;
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;

@@ -48,6 +48,9 @@ struct BmihParams {
   uint32_t r_lo;                // lowest radius of the step: radii [r_lo, radius] are probed together (normally r_lo == radius)
   uint32_t t_begin, t_end;      // ... and its tables [t_begin, t_end): a whole radius (0, m) or one table of it
   uint32_t cpi;                 // codes per work item (multiple of the step size)
+  uint32_t qt;                  // queries per work item (kBmihQT for the POPC kernel, up to 256 for the tensor-core kernel)
+  uint32_t cpi_alt, qt_alt;     // counting pass only: the item geometry of the other verify kernel ...
+  uint32_t* n_items_alt;        // ... and its item count, so that the host can choose between the two after one pass
   int max_radius;
   const TableDev* tables;       // [m]
   // per-level probe structures
@@ -118,14 +121,17 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
     const uint32_t t = b >> p.sbits, key = b & ((1u << p.sbits) - 1);
     const uint32_t* rp = p.tables[t].row_ptr;
     const uint32_t len = rp[key + 1] - rp[key];
-    const uint32_t nc = (len + p.cpi - 1) / p.cpi, nqc = (cnt + kBmihQT - 1) / kBmihQT;
+    const uint32_t nc = (len + p.cpi - 1) / p.cpi, nqc = (cnt + p.qt - 1) / p.qt;
     const uint32_t base = atomicAdd(p.n_items, nc * nqc);
-    if (!write) atomicAdd(p.bucket_codes, (unsigned long long)len);
+    if (!write) {
+      atomicAdd(p.bucket_codes, (unsigned long long)len);
+      if (p.n_items_alt) atomicAdd(p.n_items_alt, ((len + p.cpi_alt - 1) / p.cpi_alt) * ((cnt + p.qt_alt - 1) / p.qt_alt));
+    }
     if (write) {
       const uint32_t start = rp[key];
       for (uint32_t c = 0; c < nc; ++c)
         for (uint32_t qc = 0; qc < nqc; ++qc) {
-          // the bucket's query list is cut into equal chunks of at most kBmihQT queries
+          // the bucket's query list is cut into equal chunks of at most p.qt queries
           const uint32_t qlo = (uint32_t)(((uint64_t)cnt * qc) / nqc), qhi = (uint32_t)(((uint64_t)cnt * (qc + 1)) / nqc);
           BmihItem it;
           it.t = t; it.c0 = start + c * p.cpi; it.c1 = min(start + len, it.c0 + p.cpi);
