@@ -24,3 +24,4 @@ else:
     print(mode, "n", n, "B", B, "kernel_ms", ns / 1e6, "pairs/s %.3e" % (n * B / (ns * 1e-9)), "GB/s %.1f" % (n * 8 / ns),
           "grid", ix.get_param("scan.last_grid"), "qt", ix.get_param("scan.last_qt"), "occ", ix.get_param("scan.last_occ"), "stages", ix.get_param("scan.last_stages"),
           "smem", ix.get_param("scan.last_smem"), sys.argv[4:])
+print("tc units", ix.get_param("tc.last_units"), "flagged", ix.get_param("tc.last_flagged"), "hits", ix.get_param("tc.last_hits"))

@@ -82,6 +82,271 @@ __device__ __forceinline__ uint32_t op_off(uint32_t row, uint32_t kbyte) {
   return (kbyte >> 4) * LBO + (row >> 3) * SBO + (row & 7) * 16 + (kbyte & 15);
 }
 
+
+// ---- 4. the MMA issuer's loop: what does a unit cost? ------------------------------------------------------------
+// MODE 0: 2 MMAs + commit;  1: + try_wait on an already completed barrier before;  2: + tcgen05.fence::after_thread_sync;
+// MODE 3: like 2 but the wait is on a barrier completed by this loop's own commit of 4 units ago (the real dependency)
+template <int MODE>
+__global__ void __launch_bounds__(128) mma_loop_kernel(int iters, long long* clk, int n_cols) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_done, bar_sink[4];
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < (M_ + N_) * KB; i += 128) smem[i] = 0;
+  if (tid == 0) {
+    mbar_init(&bar_done, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_sink[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_done)) : "memory");     // phase 0 complete for good
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  long long t0 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(0, M_, n_cols);
+    const uint64_t ad = make_desc(smem_u32(smem), LBO, SBO), bd = make_desc(smem_u32(smem + M_ * KB), LBO, SBO);
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int s4 = it & 3;
+      if (MODE == 1 || MODE == 2) mbar_wait(&bar_done, 0);
+      if (MODE == 3 && it >= 4) mbar_wait(&bar_sink[s4], ((it >> 2) - 1) & 1);
+      if (MODE >= 2) tc_fence_after();
+      tc_mma<0>(tb + s4 * 128, ad, bd, idesc, 0);
+      tc_mma<0>(tb + s4 * 128, ad + 16, bd + 16, idesc, 1);
+      tc_commit(&bar_sink[s4]);
+    }
+    tc_commit(&bar_done);    // harmless extra arrival; just to have something to wait on below
+  }
+  __syncthreads();
+  if (tid == 0) { mbar_wait(&bar_sink[(iters - 1) & 3], ((iters - 1) >> 2) & 1); clk[blockIdx.x] = clock64() - t0; }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+
+// ---- 5. what slows the MMAs down in the real kernel?  MMA issue loop (2 x 128x64x32B + commit) with company: --------------
+// bit 0: 8 warps store 128-bit words to shared memory flat out (the expanders); bit 1: 8 warps read TMEM flat out (the epilogue);
+// bit 2: 8 warps spin on mbarrier try_wait
+__global__ void __launch_bounds__(25 * 32) mma_company_kernel(int iters, long long* clk, int company, uint32_t* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_sink[4], bar_never;
+  __shared__ uint32_t tmem_base;
+  __shared__ volatile int stop;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (uint32_t i = tid; i < 100 * 1024; i += blockDim.x) smem[i] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_sink[i], 1);
+    mbar_init(&bar_never, 1);
+    stop = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (warp == 24) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(0, M_, 64);
+      const uint64_t ad = make_desc(smem_u32(smem), 128, 512), bd = make_desc(smem_u32(smem + 8192), 128, 512);
+      const long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const int s4 = it & 3;
+        tc_mma<0>(tb + s4 * 128, ad, bd, idesc, 0);
+        tc_mma<0>(tb + s4 * 128, ad + 16, bd + 16, idesc, 1);
+        tc_commit(&bar_sink[s4]);
+      }
+      mbar_wait(&bar_sink[(iters - 1) & 3], ((iters - 1) >> 2) & 1);
+      clk[blockIdx.x] = clock64() - t0;
+      stop = 1;
+    }
+  } else if (warp < 8) {
+    if (company & 1) {
+      uint4* dst = reinterpret_cast<uint4*>(smem + 16384 + warp * 8192);
+      uint32_t v = tid;
+      while (!stop) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dst[i * 32 + lane] = make_uint4(v, v + 1, v + 2, v + 3);
+        v += 4;
+        if (company & 8) proxy_fence();
+        if (company & 16) __nanosleep(500);
+      }
+    }
+  } else if (warp < 16) {
+    if (company & 2) {
+      uint32_t acc = 0;
+      const uint32_t ta = tb + (((warp & 3) * 32) << 16) + 256;
+      while (!stop) {
+        uint32_t r[32];
+        TMEM_LD32_PACK(r, ta);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) acc = __vimax3_s16x2(acc, r[j], r[j + 1]);
+      }
+      if (acc == 0x12345678u) sink[0] = acc;
+    }
+  } else if (warp == 23) {
+    // latency probe: dependent shared-memory loads while the others are busy
+    volatile uint32_t* p32 = reinterpret_cast<volatile uint32_t*>(smem + 90 * 1024);
+    long long tsum = 0; int n = 0;
+    uint32_t idx = 0;
+    while (!stop && n < 100000) {
+      const long long a = clock64();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) idx = p32[idx & 63];
+      tsum += clock64() - a; ++n;
+    }
+    if (lane == 0) { clk[gridDim.x + blockIdx.x] = n ? tsum / n / 8 : 0; if (idx == 12345) sink[0] = idx; }
+  } else {
+    if ((company & 4) && lane == 0) {
+      while (!stop) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(&bar_never)), "r"(0u) : "memory");
+        if (ok) break;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+
+// ---- 6. operand setup: tcgen05.mma takes its operands from UNIFORM registers.  What does it cost when they change? ---------
+// MODE 0: lane 0 alone, operands change every unit (like the first production loop: R2UR per operand per MMA)
+// MODE 1: whole warp runs the loop, operands derived from the loop counter only, MMA issued under elect.sync
+// MODE 2: like 0, but the varying part of the operands goes through a reduction (redux.sync -> uniform register) ... n/a for one lane
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+template <int MODE>
+__global__ void __launch_bounds__(128) mma_operand_kernel(int iters, long long* clk, const uint32_t* perm) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_sink[4];
+  __shared__ uint32_t tmem_base;
+  __shared__ uint32_t s_perm[64];
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (uint32_t i = tid; i < 100 * 1024; i += blockDim.x) smem[i] = 0;
+  if (tid < 64) s_perm[tid] = perm[tid];
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_sink[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc(0, M_, 64);
+    const uint64_t ad0 = make_desc(smem_u32(smem), 128, 512), bd = make_desc(smem_u32(smem + 65536), 128, 512);
+    long long t0 = 0;
+    if (MODE == 0) {
+      if (lane == 0) {
+        t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+          const uint32_t as = s_perm[it & 63] & 7;                    // a value the compiler cannot prove uniform
+          const uint64_t ad = ad0 + (uint64_t)(as * 512);
+          const uint32_t dcol = tb + (it & 3) * 128;
+          tc_mma<0>(dcol, ad, bd, idesc, 0);
+          tc_mma<0>(dcol, ad + 16, bd + 16, idesc, 1);
+          if ((it & 3) == 3) tc_commit(&bar_sink[0]);
+        }
+        tc_commit(&bar_sink[1]);
+        mbar_wait(&bar_sink[1], 0);
+        clk[blockIdx.x] = clock64() - t0;
+      }
+    } else {
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t as = MODE == 1 ? (uint32_t)(it * 5) & 7 : __reduce_max_sync(0xffffffffu, s_perm[it & 63] & 7);
+        const uint64_t ad = ad0 + (uint64_t)(as * 512);
+        const uint32_t dcol = tb + (it & 3) * 128;
+        if (elect_one()) {
+          tc_mma<0>(dcol, ad, bd, idesc, 0);
+          tc_mma<0>(dcol, ad + 16, bd + 16, idesc, 1);
+          if ((it & 3) == 3) tc_commit(&bar_sink[0]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) {
+        tc_commit(&bar_sink[1]);
+        mbar_wait(&bar_sink[1], 0);
+        clk[blockIdx.x] = clock64() - t0;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+
+// ---- 7. how can the MMA thread learn that its inputs are ready without stalling behind its own MMAs? ---------------------
+// (a shared-memory load or an mbarrier try_wait by the issuing thread costs ~100-300 clocks: it waits for the MMAs in flight)
+// MODE 0: no synchronisation (reference);  MODE 1: bar.sync with a partner warp (named barrier 1) before every unit;
+// MODE 2: ld.volatile.shared of a flag before every unit;  MODE 3: ld.global of a flag before every unit
+template <int MODE>
+__global__ void __launch_bounds__(128) mma_sync_kernel(int iters, long long* clk, const uint32_t* gflag) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_sink[4];
+  __shared__ uint32_t tmem_base;
+  __shared__ volatile uint32_t s_flag;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (uint32_t i = tid; i < 100 * 1024; i += blockDim.x) smem[i] = 0;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_sink[i], 1);
+    s_flag = 1;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  if (warp == 1) {
+    const uint32_t idesc = make_idesc(0, M_, 64);
+    const uint64_t ad = make_desc(smem_u32(smem), 128, 512), bd = make_desc(smem_u32(smem + 65536), 128, 512);
+    const long long t0 = clock64();
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+      if (MODE == 1) asm volatile("bar.sync 1, 64;" ::: "memory");
+      if (MODE == 2) acc += s_flag;
+      if (MODE == 3) acc += __ldcg(gflag);
+      if (MODE == 4) { acc += s_flag; tc_fence_after(); }
+      if (MODE == 5) { uint32_t v; asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&s_flag)) : "memory"); acc += v; tc_fence_after(); }
+      if (MODE == 6) { if (lane == 0) { uint32_t v; do { asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void*)&s_flag)) : "memory"); } while (v != 1); acc += v; tc_fence_after(); } }
+      if (lane == 0 && acc != 0xFFFFFFFFu) {
+        const uint32_t dcol = tb + (it & 3) * 128;
+        tc_mma<0>(dcol, ad, bd, idesc, 0);
+        tc_mma<0>(dcol, ad + 16, bd + 16, idesc, 1);
+        tc_commit(&bar_sink[it & 3]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      mbar_wait(&bar_sink[(iters - 1) & 3], ((iters - 1) >> 2) & 1);
+      clk[blockIdx.x] = clock64() - t0;
+    }
+  } else if (warp == 2 && MODE == 1) {
+    for (int it = 0; it < iters; ++it) asm volatile("bar.sync 1, 64;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 static uint64_t sm64(uint64_t& s) { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
 // ---- 1. correctness ------------------------------------------------------------------------------------------
 template <int KIND>
@@ -246,6 +511,121 @@ static int run_check2(int n_cols) {
   }
   printf("check2 weighted encoding N=%d: %s (%d value mismatches, %d row-max mismatches)\n", n_cols, bad || badmax ? "FAIL" : "OK", bad, badmax);
   return bad + badmax;
+}
+
+
+// ---- 8. A operand from tensor memory: the expanded codes never touch shared memory ----------------------------------------
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+               "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+#define TMEM_ST16(taddr, r)                                                                                                          \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"             \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),      \
+                 "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory")
+__global__ void __launch_bounds__(128) check3_kernel(const uint64_t* codes, const uint64_t* queries, int n_cols, int32_t* out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;                      // n_cols x 64
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  uint32_t o[16];
+  for (uint32_t q = tid; q < (uint32_t)n_cols; q += 128) {
+    const uint64_t v = queries[q];
+    expand_query_word((uint32_t)v, o); expand_query_word((uint32_t)(v >> 32), o + 8);
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<uint4*>(sB + g * LBO + (q >> 3) * SBO2 + (q & 7) * 16) = make_uint4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  {
+    const uint64_t c = codes[tid];
+    expand_code_word((uint32_t)c, o); expand_code_word((uint32_t)(c >> 32), o + 8);
+    TMEM_ST16(tb + ((warp * 32) << 16) + 256, o);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(0, M_, n_cols);
+    for (int k = 0; k < 2; ++k)
+      tc_mma_ts(tb, tb + 256 + 8 * k, make_desc(smem_u32(sB) + k * 2 * LBO, LBO, SBO2), idesc, k > 0);
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < n_cols; c0 += 16) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(tb + ((warp * 32) << 16) + c0));
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) out[(size_t)tid * 256 + c0 + j] = (int32_t)r[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+static int run_check3(int n_cols) {
+  std::vector<uint64_t> codes(M_), queries(256);
+  uint64_t s = 777 + n_cols;
+  for (auto& c : codes) c = sm64(s);
+  for (auto& q : queries) q = sm64(s);
+  uint64_t *dc, *dq; int32_t* dout;
+  CK(cudaMalloc(&dc, M_ * 8)); CK(cudaMalloc(&dq, 256 * 8)); CK(cudaMalloc(&dout, M_ * 256 * 4));
+  CK(cudaMemcpy(dc, codes.data(), M_ * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dq, queries.data(), 256 * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0, M_ * 256 * 4));
+  const size_t smem = 256 * KB2;
+  CK(cudaFuncSetAttribute(check3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  check3_kernel<<<1, 128, smem>>>(dc, dq, n_cols, dout);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> out(M_ * 256);
+  CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int c = 0; c < M_; ++c)
+    for (int q = 0; q < n_cols; ++q) {
+      const int want = 64 * (64 - 2 * __builtin_popcountll(codes[c] ^ queries[q]));
+      if (out[c * 256 + q] != want && bad++ < 5) printf("  check3 mismatch c=%d q=%d got %d want %d\n", c, q, out[c * 256 + q], want);
+    }
+  printf("check3 A operand from TMEM (tcgen05.st 32x32b.x16 per row) N=%d: %s (%d mismatches)\n", n_cols, bad ? "FAIL" : "OK", bad);
+  return bad;
+}
+// MMA rate with A from TMEM
+__global__ void __launch_bounds__(128) mma_ts_rate_kernel(int iters, long long* clk, int n_cols) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  for (uint32_t i = tid; i < 256 * KB2; i += 128) smem[i] = 0;
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc(&tmem_base, 512);
+  proxy_fence();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base;
+  long long t0 = 0;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(0, M_, n_cols);
+    const uint64_t bd = make_desc(smem_u32(smem), LBO, SBO2);
+    t0 = clock64();
+    for (int it = 0; it < iters; it += 4) {
+      tc_mma_ts(tb, tb + 448, bd, idesc, 1); tc_mma_ts(tb, tb + 456, bd + 16, idesc, 1);
+      tc_mma_ts(tb + 256, tb + 464, bd, idesc, 1); tc_mma_ts(tb + 256, tb + 472, bd + 16, idesc, 1);
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) clk[blockIdx.x] = clock64() - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
 }
 
 // ---- 1b. f16 accumulators: how are they laid out in TMEM? ------------------------------------------------------------
@@ -427,6 +807,19 @@ int main(int argc, char** argv) {
   rc |= run_check<0>();
   rc |= run_check<1>();
   for (int n : {16, 48, 64, 256}) rc |= run_check2(n);
+  for (int n : {16, 64, 192}) rc |= run_check3(n);
+  {
+    long long* dck; CK(cudaMalloc(&dck, 148 * 8 * 2)); std::vector<long long> ck(sms);
+    CK(cudaFuncSetAttribute(mma_ts_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * KB2));
+    for (int n : {16, 32, 64, 128, 256}) {
+      const int iters = 4000;
+      mma_ts_rate_kernel<<<sms, 128, 256 * KB2>>>(iters, dck, n);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(ck.data(), dck, sms * 8, cudaMemcpyDeviceToHost));
+      double avg = 0; for (auto c : ck) avg += (double)c; avg /= sms;
+      printf("mma kind=i8 A from TMEM 128x%dx32B: %.1f clk per instruction\n", n, avg / iters);
+    }
+  }
   long long* dclk; uint32_t* dsink;
   CK(cudaMalloc(&dclk, sms * 8)); CK(cudaMalloc(&dsink, 4));
   std::vector<long long> clk(sms);
@@ -493,6 +886,73 @@ int main(int argc, char** argv) {
     double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
     printf("mma kind=%s 128x256x32B: %.1f clk per instruction = %.0f MAC/clk/SM, %.0f 64-bit code-query tests/clk/SM at 3 instr per tile\n",
            kind == 0 ? "i8" : "f8f6f4", avg / iters, 128.0 * 256 * 32 / (avg / iters), 128.0 * 256 / (3 * avg / iters));
+  }
+  {
+    uint32_t hperm[64]; for (int i = 0; i < 64; ++i) hperm[i] = (i * 5 + 3) & 7;
+    uint32_t* dperm; CK(cudaMalloc(&dperm, sizeof hperm)); CK(cudaMemcpy(dperm, hperm, sizeof hperm, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(mma_operand_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_operand_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_operand_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    for (int mode = 0; mode < 3; ++mode) {
+      const int iters = 4000;
+      if (mode == 0) mma_operand_kernel<0><<<sms, 128, 100 * 1024>>>(iters, dclk, dperm);
+      else if (mode == 1) mma_operand_kernel<1><<<sms, 128, 100 * 1024>>>(iters, dclk, dperm);
+      else mma_operand_kernel<2><<<sms, 128, 100 * 1024>>>(iters, dclk, dperm);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+      double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+      printf("mma operand setup mode %d (0: one lane, operands from memory; 1: whole warp, operands from the loop counter, elect; 2: whole warp, redux): %.1f clk per tile of 2 MMAs\n", mode, avg / iters);
+    }
+  }
+  {
+    uint32_t* dflag; CK(cudaMalloc(&dflag, 4)); CK(cudaMemset(dflag, 0, 4));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(mma_sync_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    for (int mode = 0; mode < 7; ++mode) {
+      const int iters = 4000;
+      if (mode == 4) mma_sync_kernel<4><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      else if (mode == 5) mma_sync_kernel<5><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      else if (mode == 6) mma_sync_kernel<6><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      else if (mode == 0) mma_sync_kernel<0><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      else if (mode == 1) mma_sync_kernel<1><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      else if (mode == 2) mma_sync_kernel<2><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      else mma_sync_kernel<3><<<sms, 128, 100 * 1024>>>(iters, dclk, dflag);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+      double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+      printf("mma + sync mode %d (0: none, 1: bar.sync with a partner warp, 2: shared-memory flag load, 3: global flag load, 4: 2 + tcgen05.fence::after, 5: ld.acquire + fence, 6: lane 0 polls ld.acquire + fence): %.1f clk per unit of 2 MMAs + commit\n", mode, avg / iters);
+    }
+  }
+  CK(cudaFuncSetAttribute(mma_company_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  {
+    long long* dclk2; CK(cudaMalloc(&dclk2, 2 * sms * 8));
+    std::vector<long long> clk2(2 * sms);
+    for (int company : {0, 1, 2, 3, 4, 7, 9, 11, 25, 27}) {
+      const int iters = 4000;
+      mma_company_kernel<<<sms, 25 * 32, 100 * 1024>>>(iters, dclk2, company, dsink);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(clk2.data(), dclk2, 2 * sms * 8, cudaMemcpyDeviceToHost));
+      double avg = 0, lat = 0; for (int i = 0; i < sms; ++i) { avg += (double)clk2[i]; lat += (double)clk2[sms + i]; } avg /= sms; lat /= sms;
+      printf("mma issue loop with company %2d (1: 8 warps STS.128, 2: 8 warps tcgen05.ld, 4: try_wait spinners, 8: + fence.proxy.async per 16 STS, 16: + 500 ns pause): %.1f clk per unit of 2 MMAs + commit; dependent LDS latency seen by another warp %.0f clk\n", company, avg / iters, lat);
+    }
+  }
+  for (int mode = 0; mode < 4; ++mode) {
+    const int iters = 4000;
+    CK(cudaFuncSetAttribute(mma_loop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(mma_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(mma_loop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(mma_loop_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (mode == 0) mma_loop_kernel<0><<<sms, 128, smem>>>(iters, dclk, 64); else if (mode == 1) mma_loop_kernel<1><<<sms, 128, smem>>>(iters, dclk, 64);
+    else if (mode == 2) mma_loop_kernel<2><<<sms, 128, smem>>>(iters, dclk, 64); else mma_loop_kernel<3><<<sms, 128, smem>>>(iters, dclk, 64);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(clk.data(), dclk, sms * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto c : clk) avg += (double)c; avg /= sms;
+    printf("mma issue loop (2 x 128x64x32B + commit per unit) mode %d: %.1f clk per unit\n", mode, avg / iters);
   }
   for (int n : {16, 32, 64, 128}) {
     const int iters = 3000;

@@ -121,9 +121,13 @@ struct vc_index {
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
-  // tensor-core verify kernel (tcverify.cuh): -1 auto, 0 never, 1 whenever legal
-  int64_t scan_tc = -1, scan_tc_min = 48, last_scan_tc = 0;
-  int64_t mih_tc = -1, mih_tc_ratio = 10, last_mih_tc_steps = 0;
+  // tensor-core verify kernel (tcverify.cuh): 0 never (default: measured slower than the POPC kernels),
+  // 1 whenever legal, -1 by size (scan: >= scan.tc_min queries; MIH: steps with >= mih.tc_ratio queries per code)
+  int64_t scan_tc = 0, scan_tc_min = 48, last_scan_tc = 0;
+  int64_t mih_tc = 0, mih_tc_ratio = 10, last_mih_tc_steps = 0;
+  int64_t tc_trace = 0;           // debug: dump CTA 0's pipeline timestamps of the last tensor-core launch to stderr
+  DevBuf b_trace;
+  int64_t tc_units = 0, tc_flagged = 0, tc_hits = 0;     // statistics of the tensor-core launches of the last search
   vc_allreduce_fn allreduce_fn = nullptr;
   void* allreduce_user = nullptr;
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
@@ -655,18 +659,14 @@ template <int W, int QT>
 static int launch_bmih_verify_tc(const BmihParams& p, int num_sms, cudaStream_t st) {
   using Cfg = TcCfg<W, QT>;
   CU(cudaFuncSetAttribute(bmih_verify_tc_kernel<W, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-  bmih_verify_tc_kernel<W, QT><<<num_sms, kTcThreads, Cfg::SMEM, st>>>(p);
+  bmih_verify_tc_kernel<W, QT><<<num_sms, Cfg::THREADS, Cfg::SMEM, st>>>(p);
   return VC_OK;
 }
 template <int W>
 static int launch_bmih_verify_tc_any(const BmihParams& p, int num_sms, cudaStream_t st) {
-  if constexpr (W == 4) {
-    return p.qt > 64 ? launch_bmih_verify_tc<4, 128>(p, num_sms, st) : launch_bmih_verify_tc<4, 64>(p, num_sms, st);
-  } else {
-    return p.qt > 64 ? launch_bmih_verify_tc<W, 256>(p, num_sms, st) : launch_bmih_verify_tc<W, 64>(p, num_sms, st);
-  }
+  return launch_bmih_verify_tc<W, 128>(p, num_sms, st);
 }
-template <int W> constexpr uint32_t tc_max_qt() { return W == 4 ? 128u : 256u; }
+template <int W> constexpr uint32_t tc_max_qt() { return 128u; }
 
 static int search_linear_ring(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, cudaStream_t st);
 
@@ -697,6 +697,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   p.tables = (const TableDev*)(sb + o_tab);
   p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
   p.bucket_codes = (unsigned long long*)(ctr + 8); p.pair_count = (unsigned long long*)(ctr + 10);
+  p.tc_stats = (unsigned long long*)(ctr + 16);
   p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
   p.gtau = (uint32_t*)(sb + o_tau); p.ghist = (uint32_t*)(sb + o_hist); p.gflag = (uint32_t*)(sb + o_flag);
   p.gradius = (uint32_t*)(sb + o_rad); p.gprobes = (unsigned long long*)(sb + o_probes); p.gcands = (unsigned long long*)(sb + o_cands);
@@ -725,6 +726,11 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   const bool pf = ix->scan_prefilter < 0 ? (W <= 2) : ix->scan_prefilter != 0;
   int grid = 0;
   if (ix->profile) cudaEventRecord(ix->ev0, st);
+  if (use_tc && ix->tc_trace) {
+    if ((rc = ix->b_trace.ensure(3 * 256 * 4 * 8))) return rc;
+    CU(cudaMemsetAsync(ix->b_trace.p, 0, 3 * 256 * 4 * 8, st));
+    p.tc_trace = (long long*)ix->b_trace.p;
+  }
   if (use_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
   else rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &grid);
   if (rc) return rc;
@@ -736,7 +742,25 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   // any overflow?  (flags are written by the append path; one small read-back)
   std::vector<uint32_t> flags(nq);
   CU(cudaMemcpyAsync(flags.data(), p.gflag, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+  unsigned long long tcs[3] = {0, 0, 0};
+  CU(cudaMemcpyAsync(tcs, p.tc_stats, 24, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  ix->tc_units = (int64_t)tcs[0]; ix->tc_flagged = (int64_t)tcs[1]; ix->tc_hits = (int64_t)tcs[2];
+  if (p.tc_trace) {
+    std::vector<long long> tr(3 * 256 * 4);
+    CU(cudaMemcpy(tr.data(), p.tc_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+    const long long t0 = tr[0];
+    fprintf(stderr, "tc trace (CTA 0)\n unit: mma: stage_free issued committed - | epilogue: t_full pass1 released hits_done | tile: expander starts, raw_full, a_empty, published\n");
+    for (int i = 0; i < 256; ++i) {
+      fprintf(stderr, "%3d:", i);
+      for (int j = 0; j < 4; ++j) fprintf(stderr, " %8lld", tr[i * 4 + j] ? tr[i * 4 + j] - t0 : -1);
+      fprintf(stderr, " |");
+      for (int j = 0; j < 4; ++j) fprintf(stderr, " %8lld", tr[(256 + i) * 4 + j] ? tr[(256 + i) * 4 + j] - t0 : -1);
+      fprintf(stderr, " |");
+      for (int j = 0; j < 4; ++j) fprintf(stderr, " %8lld", tr[(512 + i) * 4 + j] ? tr[(512 + i) * 4 + j] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   bool overflow = false;
   for (uint32_t q = 0; q < nq && !overflow; ++q) overflow = (flags[q] & 1u) != 0;
   ix->last_scan_batched = overflow ? 0 : 1;
@@ -944,6 +968,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   unsigned char* sb = (unsigned char*)ix->b_state.p;
   uint32_t* ctr = (uint32_t*)(sb + o_ctr);            // [0] n_items  [1] item_cursor  [2] n_next  [3] any_overflow
   BmihParams p;
+  memset(&p, 0, sizeof p);
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = m; p.sbits = sbits; p.radius = 0; p.max_radius = max_radius;
   p.tables = ix->d_tab; p.active = nullptr; p.n_active = 0;
   {
@@ -960,9 +985,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.bucket_codes = (unsigned long long*)(ctr + 8);
   p.pair_count = (unsigned long long*)(ctr + 10);
   p.scan_mode = 0; p.first_id = ix->first_id;
+  p.tc_stats = (unsigned long long*)(ctr + 16);
   const uint32_t popc_cpi = p.cpi;
   const bool tc_possible = ix->mih_tc != 0;
-  p.qt = kBmihQT; p.cpi_alt = kTcCpi; p.qt_alt = 64; p.n_items_alt = tc_possible ? ctr + 5 : nullptr;
+  p.qt = kBmihQT; p.cpi_alt = kTcCpi; p.qt_alt = 128; p.n_items_alt = tc_possible ? ctr + 5 : nullptr;
   ix->last_mih_tc_steps = 0;
   unsigned long long prev_codes = 0, prev_pairs = 0;
   ix->step_codes.clear(); ix->step_pairs.clear();
@@ -1034,18 +1060,18 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       step_tc = ix->mih_tc > 0 || (codes_now > 0 && pairs_now >= (double)ix->mih_tc_ratio * codes_now);
       if (step_tc) {
         p.cpi = kTcCpi;
-        if (pairs_now >= 40.0 * codes_now && tc_max_qt<W>() > 64) {
+        if (pairs_now >= 80.0 * codes_now && tc_max_qt<W>() > 128) {
           // long query lists: 256 (128) queries per item; the item count for that geometry needs its own counting pass
           p.qt = tc_max_qt<W>(); p.qt_alt = p.qt;
           CU(cudaMemsetAsync(ctr + 5, 0, 4, st));
           unsigned long long* keep_bc = p.bucket_codes; uint32_t* keep_n = p.n_items;
           p.bucket_codes = (unsigned long long*)(ctr + 6); p.n_items = ctr + 4;      // scratch: [4] is cleared before pass 1, [6..7] unused
           bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 0);
-          p.bucket_codes = keep_bc; p.n_items = keep_n; p.qt_alt = 64;
+          p.bucket_codes = keep_bc; p.n_items = keep_n; p.qt_alt = 128;
           CU(cudaMemcpyAsync(h12, ctr, 48, cudaMemcpyDeviceToHost, st));
           CU(cudaStreamSynchronize(st));
           ix->launches++;
-        } else p.qt = 64;
+        } else p.qt = 128;
         n_items = h12[5];
         ++ix->last_mih_tc_steps;
       }
@@ -1111,9 +1137,11 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     ix->launches++;
   }
   CU(cudaGetLastError());
-  unsigned long long h_bc = 0;
+  unsigned long long h_bc = 0, tcs[3] = {0, 0, 0};
   CU(cudaMemcpyAsync(&h_bc, p.bucket_codes, 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(tcs, p.tc_stats, 24, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  ix->tc_units = (int64_t)tcs[0]; ix->tc_flagged = (int64_t)tcs[1]; ix->tc_hits = (int64_t)tcs[2];
   ix->last_mih_batched = 1; ix->last_mih_levels = levels; ix->last_mih_items = items_total; ix->last_mih_bucket_codes = (int64_t)h_bc;
   return VC_OK;
 }
@@ -1213,6 +1241,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "scan.batched_min")) ix->scan_batched_min = value;
   else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
   else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
+  else if (!strcmp(name, "tc.trace")) ix->tc_trace = value;
   else if (!strcmp(name, "scan.tc")) ix->scan_tc = value;
   else if (!strcmp(name, "scan.tc_min")) ix->scan_tc_min = value;
   else if (!strcmp(name, "mih.tc")) ix->mih_tc = value;
@@ -1254,6 +1283,9 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "mih.tc")) *value = ix->mih_tc;
   else if (!strcmp(name, "mih.tc_ratio")) *value = ix->mih_tc_ratio;
   else if (!strcmp(name, "mih.last_tc_steps")) *value = ix->last_mih_tc_steps;
+  else if (!strcmp(name, "tc.last_units")) *value = ix->tc_units;
+  else if (!strcmp(name, "tc.last_flagged")) *value = ix->tc_flagged;
+  else if (!strcmp(name, "tc.last_hits")) *value = ix->tc_hits;
   else if (!strcmp(name, "mih.batched")) *value = ix->mih_batched;
   else if (!strcmp(name, "mih.last_batched")) *value = ix->last_mih_batched;
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;

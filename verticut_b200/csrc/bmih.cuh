@@ -51,6 +51,8 @@ struct BmihParams {
   uint32_t qt;                  // queries per work item (kBmihQT for the POPC kernel, up to 256 for the tensor-core kernel)
   uint32_t cpi_alt, qt_alt;     // counting pass only: the item geometry of the other verify kernel ...
   uint32_t* n_items_alt;        // ... and its item count, so that the host can choose between the two after one pass
+  long long* tc_trace;          // debug (knob tc.trace): per-unit / per-tile clock64 timestamps of CTA 0, [2][256][4]
+  unsigned long long* tc_stats; // tensor-core kernel: [0] warp x (tile, query group) units, [1] units with a flagged row, [2] hits appended
   int max_radius;
   const TableDev* tables;       // [m]
   // per-level probe structures
