@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libverticut_gpu.so")
+# VC_GPU_LIB: another build of the same ABI (A/B measurements); the default is the in-tree library
+LIB_PATH = os.environ.get("VC_GPU_LIB") or os.path.join(HERE, "lib", "libverticut_gpu.so")
 
 VC_OK, VC_NOT_FOUND = 0, 1
 VC_ERR_ARG, VC_ERR_STATE, VC_ERR_CUDA, VC_ERR_NOMEM = -1, -2, -3, -4

@@ -91,25 +91,43 @@ __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
   for (uint32_t r = p.r_lo; r <= p.radius; ++r) per_table += c_binom[p.sbits][r];
   const uint64_t per_q = (uint64_t)per_table * (p.t_end - p.t_begin);
   const uint64_t total = per_q * p.n_active;
-  for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t a = (uint32_t)(it / per_q);
-    const uint32_t rem = (uint32_t)(it % per_q);
-    const uint32_t t = p.t_begin + rem / per_table;
-    uint32_t pidx = rem % per_table, rad = p.r_lo;
-    while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
-    const uint32_t q = p.active[a];
-    const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
-    const uint32_t key = qkey ^ unrank_mask(p.sbits, rad, pidx);
-    const uint32_t* rp = p.tables[t].row_ptr;
-    const uint32_t len = rp[key + 1] - rp[key];
-    const uint32_t b = (t << p.sbits) + key;
+  const uint32_t lane = threadIdx.x & 31;
+  unsigned long long warp_pairs = 0;                          // lane 0: members of all buckets this warp probed
+  // whole warps walk the probe list (the statistics below are aggregated per warp: one atomic per distinct query and
+  // warp instead of one per probe - the probes of a query are neighbours, and 11 M atomics on one counter cost 3 ms)
+  for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < total; base += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t it = base + lane;
+    const bool valid = it < total;
+    uint32_t q = 0xFFFFFFFFu, len = 0, b = 0;
+    if (valid) {
+      const uint32_t a = (uint32_t)(it / per_q);
+      const uint32_t rem = (uint32_t)(it % per_q);
+      const uint32_t t = p.t_begin + rem / per_table;
+      uint32_t pidx = rem % per_table, rad = p.r_lo;
+      while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
+      q = p.active[a];
+      const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
+      const uint32_t key = qkey ^ unrank_mask(p.sbits, rad, pidx);
+      const uint32_t* rp = p.tables[t].row_ptr;
+      len = rp[key + 1] - rp[key];
+      b = (t << p.sbits) + key;
+    }
     if (pass == 0) {
-      if (len) { atomicAdd(&p.bcount[b], 1u); atomicAdd(&p.gcands[q], (unsigned long long)len); atomicAdd(p.pair_count, (unsigned long long)len); }
+      if (len) atomicAdd(&p.bcount[b], 1u);
+      if (__any_sync(0xffffffffu, len >= (1u << 26))) {         // giant buckets (degenerate data): 32-bit warp sums could wrap
+        if (len) { atomicAdd(&p.gcands[q], (unsigned long long)len); atomicAdd(p.pair_count, (unsigned long long)len); }
+      } else {
+        const uint32_t peers = __match_any_sync(0xffffffffu, q);
+        const uint32_t sum = __reduce_add_sync(peers, len);
+        if (valid && sum && lane == (uint32_t)__ffs(peers) - 1) atomicAdd(&p.gcands[q], (unsigned long long)sum);
+        warp_pairs += __reduce_add_sync(0xffffffffu, len);
+      }
     } else if (len) {
       const uint32_t slot = atomicAdd(&p.bcount[b], 1u);
       p.qlist[p.boffs[b] + slot] = q;
     }
   }
+  if (pass == 0 && lane == 0 && warp_pairs) atomicAdd(p.pair_count, warp_pairs);
 }
 
 // ---- 2. work items -------------------------------------------------------------------------------------------
