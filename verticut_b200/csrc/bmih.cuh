@@ -214,11 +214,19 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
   __shared__ __align__(16) uint32_t s_qrec_all[NW][kBmihQT * QS];
   __shared__ uint32_t s_qid_all[NW][kBmihQT];
   __shared__ const uint64_t* s_codes[kMaxTables];          // table payload pointers, fetched once
+  __shared__ const uint32_t* s_ids[kMaxTables];
+  __shared__ uint32_t s_cut_all[NW][kBmihQT];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < p.m) s_codes[tid] = p.tables[tid].codes;
+  if (tid < p.m) { s_codes[tid] = p.tables[tid].codes; s_ids[tid] = p.tables[tid].ids; }
   __syncthreads();
   uint32_t* s_qrec = s_qrec_all[warp];
   uint32_t* s_qid = s_qid_all[warp];
+  uint32_t* s_cut = s_cut_all[warp];
+  // Codes not found before this step have substring distance >= r + 1 in the tables before t_begin and >= r in the
+  // others: distance >= lb.  A query whose k-th best is already AT that distance can only improve by ties with a
+  // smaller id - and a bucket is in ascending id order, so that query is done with a bucket at the first id >= its
+  // k-th id (the last step of a search, table 0 of radius 3 at 1 B codes, scans ~30 % of every bucket instead of all).
+  const uint32_t lb = p.m * p.r_lo + p.t_begin;
   const uint32_t n_items = *p.n_items;
   // lane 0 runs one item ahead: the claim (atomic) and the descriptor of the next item are fetched while the
   // warp works on the current one
@@ -275,19 +283,50 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
       if (w == 0) s_qid[i] = qid;
       s_qrec[e] = w < 2 * W ? p.queries[(size_t)qid * 2 * W + w] : (w == 2 * W ? __ldcg(&p.gtau[qid]) : 0u);
     }
+    uint32_t my_cut = 0xFFFFFFFFu;
+    if (!p.scan_mode && lane < qn) {
+      const uint64_t tk = __ldcg(&p.gtaukey[p.qlist[qbeg + lane]]);
+      if ((uint32_t)(tk >> 32) == lb) my_cut = (uint32_t)tk;
+    }
+    s_cut[lane] = my_cut;
+    const bool use_cut = __any_sync(0xffffffffu, my_cut != 0xFFFFFFFFu);
+    uint32_t qlive = qn;                               // staged queries still interested in the rest of the item
     __syncwarp();
     for (uint32_t base = a0; base < c1; base += WSTEP) {
+      if (use_cut) {
+        // queries whose k-th id lies at or before the first id of this step are done with the bucket: the staged list
+        // is compacted (each query leaves once), the distance loop below stays dense
+        const uint32_t fid = __ldg(&s_ids[t][max(base, c0)]);
+        const bool keep = lane < qlive && s_cut[lane] > fid;
+        const uint32_t alive = __ballot_sync(0xffffffffu, keep);
+        if (!alive) break;
+        if (alive != (qlive >= 32 ? 0xFFFFFFFFu : ((1u << qlive) - 1u))) {
+          uint32_t rec[QS];
+#pragma unroll
+          for (int i = 0; i < QS; ++i) rec[i] = keep ? s_qrec[lane * QS + i] : 0u;
+          const uint32_t mq = keep ? s_qid[lane] : 0u, mc = keep ? s_cut[lane] : 0u;
+          __syncwarp();
+          if (keep) {
+            const uint32_t pos = __popc(alive & ((1u << lane) - 1u));
+#pragma unroll
+            for (int i = 0; i < QS; ++i) s_qrec[pos * QS + i] = rec[i];
+            s_qid[pos] = mq; s_cut[pos] = mc;
+          }
+          qlive = __popc(alive);
+          __syncwarp();
+        }
+      }
       if (base != a0) load_step(base);
       // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
       // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
       // of the codes down the slow path.  The load is issued here and consumed after this step's math.
       uint32_t fresh_tau = kInfDist;
-      if (lane < qn) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
+      if (lane < qlive) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
       QRec<W> nxt = load_qrec<W, QS>(s_qrec, 0);
 #pragma unroll 1
-      for (uint32_t q = 0; q < qn; ++q) {
+      for (uint32_t q = 0; q < qlive; ++q) {
         const QRec<W> cur = nxt;
-        if (q + 1 < qn) nxt = load_qrec<W, QS>(s_qrec, q + 1);      // next record's LDS overlaps this record's math
+        if (q + 1 < qlive) nxt = load_qrec<W, QS>(s_qrec, q + 1);      // next record's LDS overlaps this record's math
         const uint32_t* qw = cur.qw;
         const uint32_t tau = cur.tau;
         uint32_t mm[C];
@@ -309,7 +348,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
         }
       }
       __syncwarp();
-      if (lane < qn && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
+      if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
       __syncwarp();
     }
   }
