@@ -234,6 +234,7 @@ def main():
     keys_t = torch.empty((Q, K_NN), dtype=torch.int64, device=dev)
     roofline = None
     integer_pipe = None
+    exec_pairs = 0
     if mode == "mih":
         ix.search_mih_dev(dev_batches[-1].data_ptr(), Q, K_NN, keys_t.data_ptr(), d_stats=stats_t.data_ptr(),
                           stream=torch.cuda.current_stream().cuda_stream)
@@ -265,12 +266,15 @@ def main():
             sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
             popc_peak = 15.4 * ix.get_param("num_sms") * sm_hz          # tests/s at one POPC per test (prefiltered 64-bit codes)
             steps, bound_s, meas_s = [], 0.0, 0.0
+            exec_pairs = 0
             for i in range(n_steps):
                 sc, sp = ix.get_param("mih.step_codes.%d" % i), ix.get_param("mih.step_pairs.%d" % i)
+                sx = ix.get_param("mih.step_exec.%d" % i)      # tests really executed (queries leave buckets at their k-th id)
                 sn = ix.get_param("mih.step_ns.%d" % i) * 1e-9
-                t_hbm, t_popc = sc * nbytes / (peak_gbs * 1e9), sp / popc_peak
+                t_hbm, t_popc = sc * nbytes / (peak_gbs * 1e9), sx / popc_peak
+                exec_pairs += sx
                 steps.append({"hbm_ms": t_hbm * 1e3, "popc_ms": t_popc * 1e3, "measured_ms": sn * 1e3,
-                              "bound": "hbm" if t_hbm > t_popc else "popc"})
+                              "bound": "hbm" if t_hbm > t_popc else "popc", "tests_executed": sx, "bucket_members_x_queries": sp})
                 bound_s += max(t_hbm, t_popc)
                 meas_s += sn
             roofline["combined"] = {"what": "sum over search steps of max(HBM time, POPC time) / measured verify-kernel time",
@@ -283,8 +287,8 @@ def main():
                     roofline["traffic_source"] = "profiles/traffic_r01.json (ncu --set full, all verify launches of one search)"
         sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
         n_sms = ix.get_param("num_sms")
-        pairs_s = cands / k_s
-        integer_pipe = {"what": "code-query distance tests by the dominant kernel; it is POPC-bound when batched",
+        pairs_s = (exec_pairs if batched else cands) / k_s
+        integer_pipe = {"what": "code-query distance tests executed by the dominant kernel; it is POPC-bound when batched",
                         "pairs_per_s": pairs_s, "pairs_per_clk_per_sm": pairs_s / n_sms / sm_clk,
                         "popc_peak_per_clk_per_sm": 15.4, "popc_per_pair": 1 if nbytes <= 16 else nbytes // 4,
                         "frac_of_popc_peak": pairs_s / n_sms / sm_clk / 15.4 * (1 if nbytes <= 16 else nbytes // 4),

@@ -138,6 +138,7 @@ struct vc_index {
   bool ev_valid = false;
   cudaEvent_t lev[2 * 34] = {nullptr};   // batched MIH: one (start, stop) pair per radius level around the verify kernel
   int lev_used = 0;                        // > 0: last search was batched, sum these pairs
+  std::vector<int64_t> step_exec;     // ... and the tests the verify kernel really executed
   std::vector<int64_t> step_codes, step_pairs;   // per step of the last batched search: codes of distinct probed buckets, code-query tests
   // counters
   int64_t launches = 0;           // kernels launched by this index since creation
@@ -984,14 +985,15 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
   p.bucket_codes = (unsigned long long*)(ctr + 8);
   p.pair_count = (unsigned long long*)(ctr + 10);
+  p.exec_pairs = (unsigned long long*)(ctr + 12);
   p.scan_mode = 0; p.first_id = ix->first_id;
   p.tc_stats = (unsigned long long*)(ctr + 16);
   const uint32_t popc_cpi = p.cpi;
   const bool tc_possible = ix->mih_tc != 0;
   p.qt = kBmihQT; p.cpi_alt = kTcCpi; p.qt_alt = 128; p.n_items_alt = tc_possible ? ctr + 5 : nullptr;
   ix->last_mih_tc_steps = 0;
-  unsigned long long prev_codes = 0, prev_pairs = 0;
-  ix->step_codes.clear(); ix->step_pairs.clear();
+  unsigned long long prev_codes = 0, prev_pairs = 0, prev_exec = 0;
+  ix->step_codes.clear(); ix->step_pairs.clear(); ix->step_exec.clear();
   p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
   p.gtau = (uint32_t*)(sb + o_tau); p.ghist = (uint32_t*)(sb + o_hist); p.gflag = (uint32_t*)(sb + o_flag);
   p.gradius = (uint32_t*)(sb + o_rad); p.gprobes = (unsigned long long*)(sb + o_probes); p.gcands = (unsigned long long*)(sb + o_cands);
@@ -1101,14 +1103,15 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
     ix->launches += 7;
     CU(cudaGetLastError());
-    uint32_t h5[12];
-    CU(cudaMemcpyAsync(h5, ctr, 48, cudaMemcpyDeviceToHost, st));
+    uint32_t h5[14];
+    CU(cudaMemcpyAsync(h5, ctr, 56, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     {
-      unsigned long long cc, pp;
-      memcpy(&cc, h5 + 8, 8); memcpy(&pp, h5 + 10, 8);
+      unsigned long long cc, pp, xx;
+      memcpy(&cc, h5 + 8, 8); memcpy(&pp, h5 + 10, 8); memcpy(&xx, h5 + 12, 8);
       ix->step_codes.push_back((int64_t)(cc - prev_codes)); ix->step_pairs.push_back((int64_t)(pp - prev_pairs));
-      prev_codes = cc; prev_pairs = pp;
+      ix->step_exec.push_back((int64_t)(xx - prev_exec));
+      prev_codes = cc; prev_pairs = pp; prev_exec = xx;
     }
     h_ctr[3] = h5[3];
     const uint32_t n_likely = h5[4];
@@ -1291,6 +1294,11 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;
   else if (!strcmp(name, "mih.last_items")) *value = ix->last_mih_items;
   else if (!strcmp(name, "mih.last_bucket_codes")) *value = ix->last_mih_bucket_codes;
+  else if (!strncmp(name, "mih.step_exec.", 14)) {
+    const int i = atoi(name + 14);
+    if (i < 0 || i >= (int)ix->step_exec.size()) return fail(VC_ERR_ARG, "step %d out of range", i);
+    *value = ix->step_exec[i];
+  }
   else if (!strncmp(name, "mih.step_codes.", 15) || !strncmp(name, "mih.step_pairs.", 15) || !strncmp(name, "mih.step_ns.", 12)) {
     // per-step accounting of the last batched search: mih.step_codes.<i>, mih.step_pairs.<i>, mih.step_ns.<i> (verify kernel time)
     const bool is_ns = name[9] == 'n';

@@ -65,6 +65,7 @@ struct BmihParams {
   uint32_t* n_items;            // [1]
   unsigned long long* bucket_codes;   // [1] codes of all distinct probed buckets, summed over the steps (traffic accounting)
   unsigned long long* pair_count;     // [1] code-query tests = members of all probed buckets over all queries, summed over the steps
+  unsigned long long* exec_pairs;     // [1] code-query tests the verify kernel really executed (less: queries leave buckets at their k-th id)
   uint32_t* item_cursor;        // [1]
   // per-query state
   uint64_t* gbuf;               // [nq][kBmihCap]
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
   // k-th id (the last step of a search, table 0 of radius 3 at 1 B codes, scans ~30 % of every bucket instead of all).
   const uint32_t lb = p.m * p.r_lo + p.t_begin;
   const uint32_t n_items = *p.n_items;
+  unsigned long long my_pairs = 0;                     // lane 0: tests executed by this warp
   // lane 0 runs one item ahead: the claim (atomic) and the descriptor of the next item are fetched while the
   // warp works on the current one
   uint32_t next_it = n_items;
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
         }
       }
       if (base != a0) load_step(base);
+      my_pairs += (unsigned long long)(min(c1, base + WSTEP) - max(base, c0)) * qlive;
       // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
       // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
       // of the codes down the slow path.  The load is issued here and consumed after this step's math.
@@ -352,6 +355,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
       __syncwarp();
     }
   }
+  if (lane == 0 && p.exec_pairs && my_pairs) atomicAdd(p.exec_pairs, my_pairs);
 }
 
 // ---- 4. settle: per query after a step --------------------------------------------------------------------
