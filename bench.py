@@ -158,7 +158,7 @@ def main():
     import torch
     import torch.distributed as dist
     from verticut_b200 import capi
-    from verticut_b200.sharded import ShardedSearcher, shard_range
+    from verticut_b200.sharded import ShardedSearcher, shard_interleaved
 
     if not torch.cuda.is_available() or capi.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -169,10 +169,13 @@ def main():
     peak_gbs, peak_src = measured_peaks()
 
     # ---- this rank's shard: synthetic codes generated on the device, all m tables built in HBM --------
-    b, e = shard_range(n_total, world, rank)
+    # ids are dealt round-robin over the ranks (rank, rank + G, ...): every shard spans the whole id range
+    b, id_stride, n_shard = shard_interleaved(n_total, world, rank)
+    e = b + n_shard
     t0 = time.perf_counter()
     ix = capi.Index(CODE_BITS, N_TABLES, device=local_rank, first_id=b)
-    ix.add_synthetic(e - b, DB_SEED)
+    ix.set_param("id_stride", id_stride)
+    ix.add_synthetic(n_shard, DB_SEED)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
     ix.build()
@@ -381,7 +384,7 @@ def main():
                        if mode == "mih" else "exact k-NN (linear scan) k=%d over %d x %d-bit codes, batch %d" % (K_NN, n_total, CODE_BITS, Q),
                        "mode": mode, "batch": Q, "n_codes": n_total, "codes_per_gpu": e - b,
                        "l2": "inputs larger than L2 (tables %.1f GB per GPU, >= 300 MB touched per query)" % (ix.info()["device_bytes"] / 1e9),
-                       "parallelism": "id-shard x%d, NCCL all-gather top-k merge" % world},
+                       "parallelism": "id-shard x%d (ids interleaved), NCCL all-gather top-k merge, per-step all-reduce of distance / id histograms" % world},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "integer_pipe": integer_pipe, "cpu_baseline": cpu_baseline,
             "parity_selfcheck": "mih == linear scan on 8 queries: %s" % parity_ok, "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
         }

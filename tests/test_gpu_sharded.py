@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from verticut_b200 import capi
-from verticut_b200.sharded import shard_range
+from verticut_b200.sharded import shard_interleaved, shard_range
 
 pytestmark = pytest.mark.gpu
 
@@ -75,6 +75,7 @@ def test_global_threshold_hook_keeps_results_exact(oracle):
         calls.append(n_words)
 
     ixs["A"].set_allreduce(fake_allreduce)
+    ixs["A"].set_param("mih.global_key", 0)     # the second exchange (id histograms) is covered by the two-thread test below
     ida, da, ca, sta = ixs["A"].search_mih(queries, k)
     assert calls, "the hook was never called"
     ixs["A"].set_allreduce(None)
@@ -88,3 +89,110 @@ def test_global_threshold_hook_keeps_results_exact(oracle):
     np.testing.assert_array_equal(md, od)
     for ix in ixs.values():
         ix.close()
+
+
+@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("mode", ["linear", "mih"])
+def test_interleaved_shards_equal_unsharded(oracle, G, mode):
+    """Ids dealt round-robin over the shards (first_id = g, id_stride = G): same answers, and vc_code_get / the synthetic
+    generator follow the same id map."""
+    n, bits, m, nq, k = 60_001, 64, 4, 12, 100
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    lists = []
+    for g in range(G):
+        first, stride, cnt = shard_interleaved(n, G, g)
+        assert (first, stride, cnt) == (g, G, len(range(g, n, G)))
+        ix = capi.Index(bits, m, first_id=first)
+        ix.set_param("id_stride", stride)
+        if g % 2:
+            ix.add(codes[g::G])
+        else:
+            ix.add_synthetic(cnt, 12345)             # generated on the device from the global ids
+        ix.build()
+        rc, code = ix.code_get(g + 5 * G)
+        assert rc == 0 and (code == codes[g + 5 * G]).all()
+        assert ix.code_get(g + 5 * G + 1)[0] == (1 if G > 1 else 0)
+        if mode == "linear":
+            ids, dists, counts = ix.search_linear(queries, k)
+        else:
+            ix.set_param("mih.batched", g % 2)
+            ids, dists, counts, _ = ix.search_mih(queries, k)
+        assert ((ids[:, :1] - g) % G == 0).all()
+        keys = (dists.astype(np.uint64) << np.uint64(32)) | ids.astype(np.uint64)
+        keys[np.arange(k)[None, :] >= counts[:, None]] = np.uint64(capi.EMPTY_KEY)
+        lists.append(keys)
+        ix.close()
+    merged = capi.merge_topk(0, np.stack(lists), k)
+    ids, dists, counts = capi.unpack_keys(merged)
+    oid, od, oc = oracle.linear_search(codes, queries, k)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    np.testing.assert_array_equal(counts, oc)
+
+
+@pytest.mark.parametrize("table_steps", [-1, 1])
+def test_two_shards_with_live_exchange(oracle, table_steps):
+    """Both collectives of the sharded batched search, matched between two shards that search at the same time (two
+    host threads, one GPU): the per-step sum of the distance histograms and, before table-granular steps, the sum of the
+    id histograms that bounds the k-th key of the whole database.  Merged result == oracle, exactly."""
+    import threading
+    import torch
+    n, nq, k, G = 3_000_000, 64, 100, 2
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    ixs, views, results, errors = [], [None] * G, [None] * G, []
+    barrier = threading.Barrier(G)
+    n_calls = [0] * G
+    for g in range(G):
+        first, stride, cnt = shard_interleaved(n, G, g)
+        ix = capi.Index(64, 4, first_id=first)
+        ix.set_param("id_stride", stride)
+        ix.add_synthetic(cnt, 12345)
+        ix.build()
+        ix.set_param("mih.batched", 1)
+        ix.set_param("mih.table_steps", table_steps)
+        ixs.append(ix)
+
+    def make_hook(g):
+        def hook(ptr, n_words, stream):
+            class _Raw:
+                __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+            views[g] = torch.as_tensor(_Raw(), device="cuda")
+            torch.cuda.synchronize()
+            barrier.wait(timeout=60)
+            if g == 0:
+                total = views[0] + views[1]
+                views[0].copy_(total)
+                views[1].copy_(total)
+                torch.cuda.synchronize()
+            barrier.wait(timeout=60)
+            n_calls[g] += 1
+        return hook
+
+    def run(g):
+        try:
+            ixs[g].set_allreduce(make_hook(g))
+            results[g] = ixs[g].search_mih(queries, k)
+        except Exception as ex:      # a thread that dies must not leave the other one waiting
+            errors.append(ex)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert n_calls[0] == n_calls[1] and n_calls[0] >= 2
+    lists = []
+    for g in range(G):
+        ids, dists, counts, _ = results[g]
+        keys = (dists.astype(np.uint64) << np.uint64(32)) | ids.astype(np.uint64)
+        keys[np.arange(k)[None, :] >= counts[:, None]] = np.uint64(capi.EMPTY_KEY)
+        lists.append(keys)
+        ixs[g].close()
+    mi, md, mc = capi.unpack_keys(capi.merge_topk(0, np.stack(lists), k))
+    oid, od, oc = oracle.linear_search(codes, queries, k)
+    np.testing.assert_array_equal(mi, oid)
+    np.testing.assert_array_equal(md, od)

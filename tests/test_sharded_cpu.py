@@ -89,3 +89,22 @@ def test_shard_ranges_partition_the_ids():
             assert all(r[i][1] == r[i + 1][0] for i in range(g - 1))
             assert max(e - b for b, e in r) - min(e - b for b, e in r) <= 1
     assert gather_layout(8, 4096, 100) == (8, 4096, 100)
+
+
+def test_shard_maps_partition_the_ids():
+    sys.path.insert(0, ROOT)
+    from verticut_b200.sharded import shard_interleaved, shard_range
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for G in (1, 2, 3, 8):
+            seen_r, seen_i = 0, 0
+            prev_end = 0
+            for g in range(G):
+                b, e = shard_range(n, G, g)
+                assert b == prev_end and e >= b
+                prev_end = e
+                seen_r += e - b
+                first, stride, cnt = shard_interleaved(n, G, g)
+                assert stride == G and cnt == len(range(g, n, G))
+                assert cnt == 0 or (first == g and first + (cnt - 1) * stride < n)
+                seen_i += cnt
+            assert prev_end == n and seen_r == n and seen_i == n

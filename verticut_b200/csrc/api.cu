@@ -92,6 +92,7 @@ struct PinBuf {
 struct vc_index {
   int device = 0;
   uint32_t bits = 0, W = 0, m = 0, sbits = 0, first_id = 0;
+  uint32_t id_stride = 1;         // id of code j = first_id + j * id_stride: > 1 for one of G interleaved shards ("id_stride", set before adding codes)
   uint64_t n = 0, cap = 0;        // codes held / capacity (codes)
   uint64_t* d_codes = nullptr;    // main table id -> code (src/linear_search.cc:45-46), [cap][W]
   bool built = false;
@@ -102,7 +103,7 @@ struct vc_index {
   size_t smem_optin = 0;
   // scratch
   DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small, d_gstate;
-  DevBuf b_state, b_buckets, b_qlist, b_items, b_redo;   // batched MIH
+  DevBuf b_state, b_buckets, b_qlist, b_items, b_redo, b_idh;   // batched MIH
   PinBuf h_q, h_ids, h_dists, h_counts, h_stats, h_small;
   // knobs
   int64_t scan_prefilter = -1;    // -1 auto, 0 off, 1 on
@@ -121,6 +122,7 @@ struct vc_index {
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
+  int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
   // tensor-core verify kernel (tcverify.cuh): 0 never (default: measured slower than the POPC kernels),
   // 1 whenever legal, -1 by size (scan: >= scan.tc_min queries; MIH: steps with >= mih.tc_ratio queries per code)
   int64_t scan_tc = 0, scan_tc_min = 48, last_scan_tc = 0;
@@ -241,7 +243,7 @@ int vc_index_get_info(const vc_index* ix, vc_index_info* info) {
 
 // capacity is kept a multiple of 4096 codes (+ one 4096 pad) so that 128-bit loads of the last codes stay in bounds
 static int reserve_codes(vc_index* ix, uint64_t total) {
-  if (total > 0xFFFFFFFFull - ix->first_id) return fail(VC_ERR_ARG, "ids would exceed 32 bits (uint32 id, src/image_search.proto:4)");
+  if (total && (total - 1) * ix->id_stride > 0xFFFFFFFFull - ix->first_id) return fail(VC_ERR_ARG, "ids would exceed 32 bits (uint32 id, src/image_search.proto:4)");
   if (total <= ix->cap) return VC_OK;
   uint64_t want = std::max(total, ix->cap + ix->cap / 2);
   want = (want + 4095) / 4096 * 4096;
@@ -288,11 +290,11 @@ int vc_index_add_synthetic(vc_index* ix, uint64_t n, uint64_t seed) {
   int rc = reserve_codes(ix, ix->n + n);
   if (rc) return rc;
   uint64_t* dst = ix->d_codes + ix->n * ix->W;
-  const uint64_t first = (uint64_t)ix->first_id + ix->n;
+  const uint64_t first = (uint64_t)ix->first_id + ix->n * ix->id_stride;
   const int grid = grid_for(n * ix->W, 256, ix->num_sms);
-  if (ix->W == 1) synth_codes_kernel<1><<<grid, 256>>>(dst, n, first, seed);
-  else if (ix->W == 2) synth_codes_kernel<2><<<grid, 256>>>(dst, n, first, seed);
-  else synth_codes_kernel<4><<<grid, 256>>>(dst, n, first, seed);
+  if (ix->W == 1) synth_codes_kernel<1><<<grid, 256>>>(dst, n, first, ix->id_stride, seed);
+  else if (ix->W == 2) synth_codes_kernel<2><<<grid, 256>>>(dst, n, first, ix->id_stride, seed);
+  else synth_codes_kernel<4><<<grid, 256>>>(dst, n, first, ix->id_stride, seed);
   ix->launches++;
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
@@ -367,7 +369,7 @@ static int build_tables_impl(vc_index* ix) {
     CUB(cudaMalloc(&T.ids, (nalloc + 64) * 4));
     CUB(cudaMalloc(&T.codes, (nalloc + 64) * W * 8));
     ix->table_bytes += (nalloc + 64) * (4 + W * 8);
-    gather_payload_kernel<W><<<g1, 256, 0, st>>>(ix->d_codes, vs, n, ix->first_id, T.ids, T.codes);
+    gather_payload_kernel<W><<<g1, 256, 0, st>>>(ix->d_codes, vs, n, ix->first_id, ix->id_stride, T.ids, T.codes);
     ix->launches++;
     if (sbits <= 16) {
       const uint64_t nbuckets = 1ull << sbits;
@@ -430,9 +432,10 @@ int vc_index_build(vc_index* ix) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct FileHeader {
-  char magic[8];                 // "VCIX0001"
+  char magic[8];                 // "VCIX0002" (0001: no id_stride)
   uint32_t bits, m, sbits, first_id;
   uint64_t n;
+  uint32_t id_stride, reserved;
 };
 struct TableHeader { uint32_t sparse, n_unique; uint64_t row_ptr_entries; };
 const size_t kIoChunk = (size_t)64 << 20;
@@ -463,8 +466,9 @@ int vc_index_save(vc_index* ix, const char* path) {
   if (!f) return fail(VC_ERR_ARG, "cannot open %s for writing", path);
   std::vector<char> stage(kIoChunk);
   FileHeader h;
-  memcpy(h.magic, "VCIX0001", 8);
+  memcpy(h.magic, "VCIX0002", 8);
   h.bits = ix->bits; h.m = ix->m; h.sbits = ix->sbits; h.first_id = ix->first_id; h.n = ix->n;
+  h.id_stride = ix->id_stride; h.reserved = 0;
   int rc = fwrite(&h, sizeof h, 1, f) == 1 ? VC_OK : fail(VC_ERR_STATE, "short write");
   if (!rc && ix->n) rc = dev_to_file(f, ix->d_codes, ix->n * ix->W * 8, stage);
   for (uint32_t t = 0; t < ix->m && !rc; ++t) {
@@ -489,11 +493,12 @@ int vc_index_load(int device, const char* path, vc_index** out) {
   FILE* f = fopen(path, "rb");
   if (!f) return fail(VC_ERR_ARG, "cannot open %s", path);
   FileHeader h;
-  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "VCIX0001", 8) != 0) { fclose(f); return fail(VC_ERR_ARG, "%s is not a verticut index file", path); }
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "VCIX0002", 8) != 0) { fclose(f); return fail(VC_ERR_ARG, "%s is not a verticut index file", path); }
   vc_index* ix = nullptr;
   int rc = vc_index_create(device, h.bits, h.m, h.first_id, &ix);
   if (rc) { fclose(f); return rc; }
-  if (ix->sbits != h.sbits) { fclose(f); vc_index_destroy(ix); return fail(VC_ERR_ARG, "corrupt header"); }
+  if (ix->sbits != h.sbits || h.id_stride == 0) { fclose(f); vc_index_destroy(ix); return fail(VC_ERR_ARG, "corrupt header"); }
+  ix->id_stride = h.id_stride;
   DeviceGuard g(device);
   std::vector<char> stage(kIoChunk);
   rc = reserve_codes(ix, std::max<uint64_t>(h.n, 1));
@@ -556,9 +561,9 @@ int vc_bucket_get(vc_index* ix, uint32_t table, uint32_t index, uint32_t* ids, v
 
 int vc_code_get(vc_index* ix, uint32_t id, void* code) {
   if (!ix || !code) return fail(VC_ERR_ARG, "null argument");
-  if (id < ix->first_id || (uint64_t)id - ix->first_id >= ix->n) return VC_NOT_FOUND;
+  if (id < ix->first_id || (id - ix->first_id) % ix->id_stride != 0 || (uint64_t)(id - ix->first_id) / ix->id_stride >= ix->n) return VC_NOT_FOUND;
   DeviceGuard g(ix->device);
-  CU(cudaMemcpy(code, ix->d_codes + (uint64_t)(id - ix->first_id) * ix->W, ix->W * 8, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(code, ix->d_codes + (uint64_t)((id - ix->first_id) / ix->id_stride) * ix->W, ix->W * 8, cudaMemcpyDeviceToHost));
   return VC_OK;
 }
 
@@ -690,7 +695,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   BmihParams p;
   memset(&p, 0, sizeof p);
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = 1; p.sbits = 0; p.max_radius = 0;
-  p.scan_mode = 1; p.first_id = ix->first_id;
+  p.scan_mode = 1; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
   TableDev pseudo;
   memset(&pseudo, 0, sizeof pseudo);
   pseudo.codes = ix->d_codes;
@@ -817,7 +822,7 @@ static int search_linear_ring(vc_index* ix, const void* d_queries, uint32_t nq, 
   const int hb = W == 1 ? ScanCfg<1>::HB : W == 2 ? ScanCfg<2>::HB : ScanCfg<4>::HB;
   const uint32_t step = W == 1 ? ScanCfg<1>::STEP : W == 2 ? ScanCfg<2>::STEP : ScanCfg<4>::STEP;
   ScanParams p;
-  p.codes = (const uint4*)ix->d_codes; p.n = ix->n; p.first_id = ix->first_id;
+  p.codes = (const uint4*)ix->d_codes; p.n = ix->n; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k;
   p.BUF = pow2_at_least(k + kScanSub);
   p.compact_at = k + (p.BUF - k) / 2;
@@ -962,7 +967,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
                o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
                o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
-               o_xhist = take((size_t)nq * Cfg::HB * 4),
+               o_xhist = take((size_t)nq * Cfg::HB * 4), o_globkey = take((size_t)nq * 8),
                o_ctr = take(128);   // [0] n_items [1] item_cursor [2] n_next [3] any_overflow [4] n_likely [8..9] bucket_codes
   if ((rc = ix->b_state.ensure(off))) return rc;
   if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024))) return rc;
@@ -986,7 +991,8 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.bucket_codes = (unsigned long long*)(ctr + 8);
   p.pair_count = (unsigned long long*)(ctr + 10);
   p.exec_pairs = (unsigned long long*)(ctr + 12);
-  p.scan_mode = 0; p.first_id = ix->first_id;
+  p.scan_mode = 0; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
+  p.gglobkey = ix->allreduce_fn ? (uint64_t*)(sb + o_globkey) : nullptr;
   p.tc_stats = (unsigned long long*)(ctr + 16);
   const uint32_t popc_cpi = p.cpi;
   const bool tc_possible = ix->mih_tc != 0;
@@ -1125,6 +1131,19 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       // next radius: one table at a time if most of the remaining queries would stop inside it anyway
       granular = max_radius < 0 && (ix->mih_table_steps > 0 || (ix->mih_table_steps < 0 && (uint64_t)n_likely * 2 >= n_active));
     }
+    if (ix->allreduce_fn && granular && n_active > 0 && r <= sbits && ix->mih_global_key != 0) {
+      // id-sharded search, next step one table of a radius: most queries' k-th distance now equals the distance bound of
+      // what is left to find, so the k-th ID of the whole database decides what can still matter (bmih_idhist_kernel)
+      const uint32_t lb_next = m * r + t0;
+      const size_t words = (size_t)nq * (kIdBins + 1);
+      if ((rc = ix->b_idh.ensure(words * 4))) return rc;
+      uint32_t* idh = (uint32_t*)ix->b_idh.p;
+      CU(cudaMemsetAsync(idh, 0, words * 4, st));
+      bmih_idhist_kernel<<<(n_active * 32 + 255) / 256, 256, 0, st>>>(p, cur, n_active, lb_next, idh);
+      if (ix->allreduce_fn(ix->allreduce_user, idh, (uint64_t)words, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+      bmih_idcut_kernel<<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, lb_next, idh);
+      ix->launches += 2;
+    }
   }
   if (ix->profile) { ix->lev_used = std::min(levels, 34); ix->ev_valid = true; }
   (void)first_verify;
@@ -1244,11 +1263,17 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "scan.batched_min")) ix->scan_batched_min = value;
   else if (!strcmp(name, "scan.smem_kb")) ix->scan_smem_kb = value;
   else if (!strcmp(name, "merge.fanin")) ix->merge_fanin = value;
+  else if (!strcmp(name, "id_stride")) {
+    if (value < 1 || value > 65536) return fail(VC_ERR_ARG, "id_stride must be in [1, 65536]");
+    if (ix->n) return fail(VC_ERR_STATE, "id_stride must be set before codes are added");
+    ix->id_stride = (uint32_t)value;
+  }
   else if (!strcmp(name, "tc.trace")) ix->tc_trace = value;
   else if (!strcmp(name, "scan.tc")) ix->scan_tc = value;
   else if (!strcmp(name, "scan.tc_min")) ix->scan_tc_min = value;
   else if (!strcmp(name, "mih.tc")) ix->mih_tc = value;
   else if (!strcmp(name, "mih.tc_ratio")) ix->mih_tc_ratio = value;
+  else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
   else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
@@ -1281,6 +1306,7 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "scan.last_stages")) *value = ix->last_scan_stages;
   else if (!strcmp(name, "scan.stages")) *value = ix->scan_stages;
   else if (!strcmp(name, "num_sms")) *value = ix->num_sms;
+  else if (!strcmp(name, "id_stride")) *value = ix->id_stride;
   else if (!strcmp(name, "scan.tc")) *value = ix->scan_tc;
   else if (!strcmp(name, "scan.last_tc")) *value = ix->last_scan_tc;
   else if (!strcmp(name, "mih.tc")) *value = ix->mih_tc;

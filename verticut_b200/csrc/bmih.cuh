@@ -71,6 +71,7 @@ struct BmihParams {
   uint64_t* gbuf;               // [nq][kBmihCap]
   uint32_t* gcnt;               // [nq]
   uint64_t* gtaukey;            // [nq]
+  uint64_t* gglobkey;           // [nq] id-sharded search: a key that at least k codes of the WHOLE database are below (or kEmptyKey)
   uint32_t* gtau;               // [nq]
   uint32_t* ghist;              // [nq][HB]
   uint32_t* gflag;              // [nq] bit0 = buffer overflowed (redo with the per-query kernel), bit1 = finished
@@ -81,7 +82,7 @@ struct BmihParams {
   uint32_t* n_next;             // [1]
   // brute-force scan through the same machinery: one pseudo table (the main code array in id order, ids = first_id +
   // position), one "bucket" = the whole shard, every query in its list; no de-duplication needed
-  uint32_t scan_mode, first_id;
+  uint32_t scan_mode, first_id, id_stride;
 };
 
 // ---- 1. probes of one level -------------------------------------------------------------------------------
@@ -185,7 +186,7 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
       if (sd < r_own || (sd == r_own && t2 < t)) return;
     }
   }
-  const uint64_t key = pack_key(d, p.scan_mode ? p.first_id + j : p.tables[t].ids[j]);
+  const uint64_t key = pack_key(d, p.scan_mode ? p.first_id + j * p.id_stride : p.tables[t].ids[j]);
   if (key >= __ldcg(&p.gtaukey[qid])) return;
   const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
   if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   }
   if (tid == 0) {
     p.gcnt[q] = kept;
-    p.gtaukey[q] = tk;
+    p.gtaukey[q] = p.gglobkey ? min(tk, p.gglobkey[q]) : tk;
     if (tk != kEmptyKey) atomicMin(&p.gtau[q], (uint32_t)(tk >> 32));
   }
 }
@@ -436,11 +437,51 @@ __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uin
   else p.next_active[atomicAdd(p.n_next, 1u)] = q;
 }
 
+// ---- id-sharded search: a bound on the k-th KEY of the whole database ------------------------------------------
+// The all-reduced distance histograms give every shard the k-th DISTANCE tau of the whole database.  When the next step
+// can only add codes at exactly that distance (lb_next == tau, see bmih_verify_kernel), what matters is the k-th ID among
+// them - and a shard's own k-th key says little about it.  So the shards sum, per such query, the number of their kept
+// codes below tau and a histogram of the ids (top 8 bits) of those at tau (same all-reduce callback); the first bin
+// edge at which k codes are reached is a key that k codes of the database are below: candidates at or above it cannot be
+// in the answer, whichever shard finds them.  With ids interleaved over the shards every shard then leaves its buckets
+// at ~ the same fraction as a single GPU would.
+constexpr int kIdBins = 256;
+__global__ void bmih_idhist_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, uint32_t lb_next, uint32_t* idh) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_list) return;
+  const uint32_t q = list[w];
+  const uint32_t tau = p.gtau[q];
+  if (tau != lb_next) return;
+  uint32_t* row = idh + (size_t)q * (kIdBins + 1);
+  const uint32_t n = min(p.gcnt[q], p.k);
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint64_t key = p.gbuf[(size_t)q * kBmihCap + i];
+    const uint32_t d = (uint32_t)(key >> 32);
+    if (d < tau) atomicAdd(&row[0], 1u);
+    else if (d == tau) atomicAdd(&row[1 + ((uint32_t)key >> 24)], 1u);
+  }
+}
+__global__ void bmih_idcut_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, uint32_t lb_next, const uint32_t* idh) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_list) return;
+  const uint32_t q = list[i];
+  if (p.gtau[q] != lb_next) return;
+  const uint32_t* row = idh + (size_t)q * (kIdBins + 1);
+  uint32_t cum = row[0];
+  uint64_t bound = kEmptyKey;
+  for (uint32_t b = 0; b < (uint32_t)kIdBins; ++b) {
+    cum += row[1 + b];
+    if (cum >= p.k) { bound = b + 1 == (uint32_t)kIdBins ? pack_key(lb_next + 1, 0) : pack_key(lb_next, (b + 1) << 24); break; }
+  }
+  if (bound < p.gglobkey[q]) p.gglobkey[q] = bound;
+  if (bound < p.gtaukey[q]) p.gtaukey[q] = bound;
+}
+
 // per-query state at the start of a search
 __global__ void bmih_init_kernel(const BmihParams p, uint32_t* active0) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= p.nq) return;
-  p.gcnt[q] = 0; p.gtau[q] = kInfDist; p.gtaukey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
+  p.gcnt[q] = 0; p.gtau[q] = kInfDist; p.gtaukey[q] = kEmptyKey; if (p.gglobkey) p.gglobkey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
   p.gprobes[q] = 0; p.gcands[q] = 0;
   active0[q] = q;
 }

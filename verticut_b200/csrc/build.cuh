@@ -213,22 +213,22 @@ __global__ void dense_bitmap_kernel(const uint32_t* __restrict__ row_ptr, uint64
   }
 }
 
-// payload in bucket order: ids[j] = first_id + perm[j], codes[j] = main[perm[j]]
+// payload in bucket order: ids[j] = first_id + perm[j] * id_stride, codes[j] = main[perm[j]]
 template <int W>
 __global__ void gather_payload_kernel(const uint64_t* __restrict__ main_codes, const uint32_t* __restrict__ perm, uint64_t n,
-                                      uint32_t first_id, uint32_t* __restrict__ ids, uint64_t* __restrict__ codes) {
+                                      uint32_t first_id, uint32_t id_stride, uint32_t* __restrict__ ids, uint64_t* __restrict__ codes) {
   for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t o = perm[j];
-    ids[j] = first_id + o;
+    ids[j] = first_id + o * id_stride;
 #pragma unroll
     for (int w = 0; w < W; ++w) codes[j * W + w] = main_codes[(uint64_t)o * W + w];
   }
 }
 
 template <int W>
-__global__ void synth_codes_kernel(uint64_t* __restrict__ codes, uint64_t n, uint64_t first_id, uint64_t seed) {
+__global__ void synth_codes_kernel(uint64_t* __restrict__ codes, uint64_t n, uint64_t first_id, uint64_t id_stride, uint64_t seed) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * W; i += (uint64_t)gridDim.x * blockDim.x)
-    codes[i] = synth_word(seed, first_id + i / W, (uint32_t)(i % W));
+    codes[i] = synth_word(seed, first_id + (i / W) * id_stride, (uint32_t)(i % W));
 }
 
 }  // namespace vc

@@ -39,6 +39,7 @@ struct ScanParams {
   const uint4* codes;        // shard codes, [n][W] u64, 16-byte aligned, padded
   uint64_t n;                // codes in the shard
   uint32_t first_id;         // global id of code 0
+  uint32_t id_stride;        // id of code j = first_id + j * id_stride (1, or the number of interleaved shards)
   const uint32_t* queries;   // [nq][2W] u32
   uint32_t nq, k;
   uint32_t QT;               // queries per CTA
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanPa
               const uint32_t d = PREFILTER ? hamming_exact<W>(code[c].w, qw) : m[c];
               const uint64_t idx = base + local_of(c);
               if (d <= tau && idx < end) {
-                scan_append(smem_raw, p.QT, BUF, S, QS, HB, 2 * W, p.k, q, d, p.first_id + (uint32_t)idx,
+                scan_append(smem_raw, p.QT, BUF, S, QS, HB, 2 * W, p.k, q, d, p.first_id + (uint32_t)idx * p.id_stride,
                             p.gtau + q0 + q, p.ghist + (size_t)(q0 + q) * HB);
                 appended = 1;
               }
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanPa
       for (int c = 0; c < C; ++c) {
         const uint64_t idx = base + local_of(c);
         const bool valid = idx < end;
-        const uint32_t id = p.first_id + (uint32_t)idx;
+        const uint32_t id = p.first_id + (uint32_t)idx * p.id_stride;
         for (uint32_t half = 0; half < kScanThreads / kScanSub; ++half) {
           for (uint32_t q = warp; q < nq_here; q += kScanWarps) {
             if (s.flag[q] && s.cnt[q] + kScanSub > BUF) {

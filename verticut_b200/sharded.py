@@ -29,6 +29,16 @@ def shard_range(n_total, world_size, rank):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
+def shard_interleaved(n_total, world_size, rank):
+    """(first_id, id_stride, count) of the ids owned by `rank` when ids are dealt round-robin: rank, rank + G, ...
+    Every shard then spans the whole id range, which is what lets all of them leave a bucket at the k-th id of the whole
+    database (bmih.cuh) instead of only the shards that own small ids; create the index with first_id = rank and
+    set_param("id_stride", G) before adding codes."""
+    n_total, world_size, rank = int(n_total), int(world_size), int(rank)
+    count = (n_total - rank + world_size - 1) // world_size if rank < n_total else 0
+    return rank, world_size, count
+
+
 def gather_layout(world_size, nq, k):
     """Shape of the all-gathered buffer the merge kernel consumes: [n_lists = G][nq][k] packed words."""
     return (world_size, nq, k)
@@ -65,7 +75,7 @@ class ShardedSearcher:
             class _Raw:            # zero-copy view of library-owned device memory
                 __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
             view = t.as_tensor(_Raw(), device=t.device("cuda", self.index.device))
-            self._views = {key: view}
+            self._views[key] = view
         self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
 
     def _buffers(self, nq, k, device):
