@@ -156,13 +156,20 @@ int vc_merge_topk(int device, const uint64_t* lists, uint32_t n_lists, uint32_t 
  * n_words uint32 words at device address d_words (an all-reduce; enqueued on `stream` or ordered after it) and
  * return 0.  When set, the batched MIH search calls it once per search step on its per-query distance
  * histograms, which lets every shard filter and stop on the k-th distance of the whole database instead of its
- * own (fewer probes per shard; all shards then take the same steps, so the collective is matched).  Replaces the
- * per-radius MPI_Gatherv / MPI_Bcast pair of src/search_worker.cc:177,207.  fn = NULL (default): no exchange. */
+ * own (fewer probes per shard; all shards then take the same steps, so the collective is matched), and, before a
+ * table-granular step, on per-query id histograms that bound the k-th (distance, id) key of the whole database
+ * ("mih.global_key", default 1).  Replaces the per-radius MPI_Gatherv / MPI_Bcast pair of
+ * src/search_worker.cc:177,207.  fn = NULL (default): no exchange. */
 typedef int (*vc_allreduce_fn)(void* user, uint32_t* d_words, uint64_t n_words, void* stream);
 int vc_index_set_allreduce(vc_index* ix, vc_allreduce_fn fn, void* user);
 
-/* Tuning / introspection knobs (integers), e.g. "scan.prefilter", "scan.variant", "scan.waves",
- * "mih.threads".  Unknown names return VC_ERR_ARG.  vc_get_counter reads back launch counts etc. */
+/* Knobs and counters (integers).  Unknown names return VC_ERR_ARG.
+ *   "id_stride"   id of the j-th code added = first_id + j * id_stride (default 1; G for one of G interleaved shards;
+ *                 must be set before codes are added; stored by vc_index_save)
+ *   "scan.*", "mih.*"   kernel selection and tuning, e.g. "scan.batched", "scan.prefilter", "mih.batched",
+ *                 "mih.table_steps", "mih.global_key"; "scan.tc" / "mih.tc" = 1 route the distance filter through the
+ *                 tensor-core kernel (off by default: measured slower)
+ *   "profile", "last_kernel_ns", "launches", "mih.step_*", "tc.last_*"   read-back of timings and statistics */
 int vc_index_set_param(vc_index* ix, const char* name, int64_t value);
 int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value);
 
