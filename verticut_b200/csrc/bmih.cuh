@@ -30,6 +30,7 @@ constexpr int kBmihThreads = 256;
 constexpr int kBmihQT = 32;          // queries per work item
 constexpr int kBmihCap = 4096;       // candidate-buffer entries per query
 constexpr int kBmihU4 = 4;           // 128-bit loads per thread per step (short-bucket variant)
+constexpr int kPfDist = 4;           // L2 prefetch distance of the verify kernel, in warp steps of 2 KB
 
 template <int W, int U4 = kBmihU4> struct BmihCfg {
   static constexpr int C = 2 * U4 / W;                      // codes per thread per step (U4 = 4: 8 / 4 / 2)
@@ -279,6 +280,14 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
       else return c * 32 + lane;
     };
     load_step(a0);                                     // the first codes travel while the queries are staged
+    {
+      // ... and so do the next kPfDist - 1 steps, into L2 (two lines per lane and step)
+#pragma unroll
+      for (int s1 = 1; s1 < kPfDist; ++s1) {
+        const uint32_t u = (uint32_t)s1 * 128 + (lane & 15) * 8;
+        if (lane < 16 && u < u4_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + u));
+      }
+    }
     __syncwarp();                                      // previous item's readers are done with the warp's slice
     for (uint32_t e = lane; e < qn * QS; e += 32) {
       const uint32_t i = e / QS, w = e % QS;
@@ -320,35 +329,51 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
         }
       }
       if (base != a0) load_step(base);
+      {
+        // the codes kPfDist steps ahead on their way into L2 (a warp step is 2 KB = 16 lines; no registers needed)
+        const uint32_t ahead = (base - a0 + kPfDist * WSTEP) * W / 2;
+        if (lane < 16 && ahead + lane * 8 < u4_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ahead + lane * 8));
+      }
       my_pairs += (unsigned long long)(min(c1, base + WSTEP) - max(base, c0)) * qlive;
       // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
       // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
       // of the codes down the slow path.  The load is issued here and consumed after this step's math.
       uint32_t fresh_tau = kInfDist;
       if (lane < qlive) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
-      QRec<W> nxt = load_qrec<W, QS>(s_qrec, 0);
-#pragma unroll 1
-      for (uint32_t q = 0; q < qlive; ++q) {
-        const QRec<W> cur = nxt;
-        if (q + 1 < qlive) nxt = load_qrec<W, QS>(s_qrec, q + 1);      // next record's LDS overlaps this record's math
-        const uint32_t* qw = cur.qw;
+      // one staged query against this thread's C codes: the minimum of the (lower-bound) distances decides; the rare
+      // hit recomputes per code
+      auto test_query = [&](const QRec<W>& cur, uint32_t q) {
         const uint32_t tau = cur.tau;
-        uint32_t mm[C];
-        uint32_t mn = 0xFFFFFFFFu;
+        uint32_t mn;
+        if constexpr (C >= 3) {
+          mn = PREFILTER ? hamming_lower_bound<W>(code[0].w, cur.qw) : hamming_exact<W>(code[0].w, cur.qw);
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          mm[c] = PREFILTER ? hamming_lower_bound<W>(code[c].w, qw) : hamming_exact<W>(code[c].w, qw);
-          mn = min(mn, mm[c]);
+          for (int c = 1; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
+        } else {
+          mn = 0xFFFFFFFFu;
+#pragma unroll
+          for (int c = 0; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
         }
         if (mn <= tau) {
+          uint32_t qq = q;
+          asm volatile("" : "+r"(qq));        // keeps the address arithmetic of this rare path out of the loop body
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            if (mm[c] <= tau) {
-              const uint32_t d = PREFILTER ? hamming_exact<W>(code[c].w, qw) : mm[c];
-              const uint32_t j = base + local_of(c);
-              if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[q], t, d, j, code[c], s_qrec + q * QS, tau);
-            }
+            const uint32_t d = hamming_exact<W>(code[c].w, cur.qw);
+            const uint32_t j = base + local_of(c);
+            if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[qq], t, d, j, code[c], s_qrec + qq * QS, tau);
           }
+        }
+      };
+      // two records in flight, ping-pong: the next record's LDS overlaps this record's math, without register moves
+      QRec<W> ra = load_qrec<W, QS>(s_qrec, 0), rb;
+#pragma unroll 1
+      for (uint32_t q = 0; q < qlive; q += 2) {
+        if (q + 1 < qlive) rb = load_qrec<W, QS>(s_qrec, q + 1);
+        test_query(ra, q);
+        if (q + 1 < qlive) {
+          if (q + 2 < qlive) ra = load_qrec<W, QS>(s_qrec, q + 2);
+          test_query(rb, q + 1);
         }
       }
       __syncwarp();

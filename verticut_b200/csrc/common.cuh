@@ -93,11 +93,19 @@ __device__ __forceinline__ uint32_t hamming_exact(const uint32_t* __restrict__ c
   return d;
 }
 // Lower bound of the distance with half the POPCs: popc(x | y) <= popc(x) + popc(y).
+// Two LOP3 per 64 bits: t = a ^ b, then (c ^ d) | t as ONE three-input LOP3 (LUT 0xBE).  Written in PTX because the
+// compiler otherwise keeps both XORs as separate instructions to share them with the exact path (3 LOP3 per test: the ALU
+// pipe, not the POPC pipe, then bounds the loop).
+__device__ __forceinline__ uint32_t xor_or(uint32_t a, uint32_t b, uint32_t t) {
+  uint32_t y;
+  asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(y) : "r"(a), "r"(b), "r"(t));
+  return y;
+}
 template <int W>
 __device__ __forceinline__ uint32_t hamming_lower_bound(const uint32_t* __restrict__ c, const uint32_t* __restrict__ q) {
   uint32_t d = 0;
 #pragma unroll
-  for (int i = 0; i < W; ++i) d += __popc((c[2 * i] ^ q[2 * i]) | (c[2 * i + 1] ^ q[2 * i + 1]));
+  for (int i = 0; i < W; ++i) d += __popc(xor_or(c[2 * i + 1], q[2 * i + 1], c[2 * i] ^ q[2 * i]));
   return d;
 }
 
