@@ -359,9 +359,12 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
           asm volatile("" : "+r"(qq));        // keeps the address arithmetic of this rare path out of the loop body
 #pragma unroll
           for (int c = 0; c < C; ++c) {
-            const uint32_t d = hamming_exact<W>(code[c].w, cur.qw);
-            const uint32_t j = base + local_of(c);
-            if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[qq], t, d, j, code[c], s_qrec + qq * QS, tau);
+            // the cheap bound again first (the minimum above did not say which code): one POPC, not two, for the rest
+            if (!PREFILTER || hamming_lower_bound<W>(code[c].w, cur.qw) <= tau) {
+              const uint32_t d = hamming_exact<W>(code[c].w, cur.qw);
+              const uint32_t j = base + local_of(c);
+              if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[qq], t, d, j, code[c], s_qrec + qq * QS, tau);
+            }
           }
         }
       };
