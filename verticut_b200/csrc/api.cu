@@ -1012,8 +1012,13 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));      // histograms count this search's candidates only
   CU(cudaMemsetAsync(xhist, 0, (size_t)nq * Cfg::HB * 4, st));
   bmih_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p, actA);
-  bmih_bootstrap_kernel<W><<<(nq + 7) / 8, 256, 0, st>>>(p);
+  bmih_bootstrap_kernel<W><<<(nq + 7) / 8, 256, 0, st>>>(p, ix->allreduce_fn ? xhist : nullptr);
   ix->launches += 2;
+  if (ix->allreduce_fn) {
+    if (ix->allreduce_fn(ix->allreduce_user, xhist, (uint64_t)nq * Cfg::HB, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+    bmih_boot_tau_kernel<W><<<(nq + 127) / 128, 128, 0, st>>>(p, xhist);
+    ix->launches++;
+  }
   uint32_t h_ctr[4] = {0, 0, 0, 0};
   uint32_t n_active = nq;
   uint32_t* cur = actA;

@@ -521,7 +521,7 @@ __global__ void bmih_init_kernel(const BmihParams p, uint32_t* active0) {
 // a valid bound, since these are real database codes that level 0 will find again.
 constexpr uint32_t kBmihSample = 4096;     // at least; 16 * k when that is more
 template <int W>
-__global__ void __launch_bounds__(256) bmih_bootstrap_kernel(const BmihParams p) {
+__global__ void __launch_bounds__(256) bmih_bootstrap_kernel(const BmihParams p, uint32_t* xh /* id-sharded: the sample histograms, to be summed over the shards */) {
   constexpr int HB = BmihCfg<W>::HB;
   __shared__ uint32_t s_hist[8][HB];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -556,12 +556,26 @@ __global__ void __launch_bounds__(256) bmih_bootstrap_kernel(const BmihParams p)
     taken += take;
   }
   __syncwarp();
+  if (xh) for (uint32_t i = lane; i < HB; i += 32) xh[(size_t)q * HB + i] = h[i];
   if (lane == 0) {
     uint32_t cum = 0;
     for (uint32_t d = 0; d <= 64 * W; ++d) {
       cum += h[d];
       if (cum >= p.k) { p.gtau[q] = d; break; }
     }
+  }
+}
+// id-sharded search: the shards' samples are disjoint sets of real codes, so the k-th smallest distance of their union
+// bounds the k-th distance of the whole database - G times the sample, a much tighter start than a shard's own
+template <int W>
+__global__ void bmih_boot_tau_kernel(const BmihParams p, const uint32_t* xh) {
+  constexpr int HB = BmihCfg<W>::HB;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= p.nq) return;
+  uint32_t cum = 0;
+  for (uint32_t d = 0; d <= 64 * W; ++d) {
+    cum += xh[(size_t)q * HB + d];
+    if (cum >= p.k) { atomicMin(&p.gtau[q], d); break; }
   }
 }
 
