@@ -1,1 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_bmih.py tests/test_gpu_tc.py tests/test_gpu_sharded.py -x -q -m gpu 2>&1 | tail -3
+VC_BENCH_Q=4096 VC_BENCH_SKIP_CPU=1 VC_BENCH_SKIP_BIG_SCAN=1 timeout 300 python bench.py --steps 4 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readline())
+print('value', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', round(d['ms_per_step'],2), 'verify_ms', round(d['roofline']['kernel_ms'],2), 'launches', d['gpu_launches'], d['parity_selfcheck'])
+"

@@ -138,19 +138,43 @@ __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
 template <int W>
 __global__ void bmih_items_kernel(const BmihParams p, int write) {
   const uint32_t n_buckets = p.m << p.sbits;
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
-    const uint32_t cnt = p.boffs[b + 1] - p.boffs[b];
-    if (!cnt) continue;
-    const uint32_t t = b >> p.sbits, key = b & ((1u << p.sbits) - 1);
-    const uint32_t* rp = p.tables[t].row_ptr;
-    const uint32_t len = rp[key + 1] - rp[key];
-    const uint32_t nc = (len + p.cpi - 1) / p.cpi, nqc = (cnt + p.qt - 1) / p.qt;
-    const uint32_t base = atomicAdd(p.n_items, nc * nqc);
-    if (!write) {
-      atomicAdd(p.bucket_codes, (unsigned long long)len);
-      if (p.n_items_alt) atomicAdd(p.n_items_alt, ((len + p.cpi_alt - 1) / p.cpi_alt) * ((cnt + p.qt_alt - 1) / p.qt_alt));
+  const uint32_t lane = threadIdx.x & 31;
+  // whole warps walk the bucket list: item positions are claimed with one atomic per warp (prefix sum over the lanes),
+  // the statistics are summed per warp (170 K atomics on one counter made this kernel 80 us instead of ~15)
+  for (uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; b0 < n_buckets; b0 += gridDim.x * blockDim.x) {
+    const uint32_t b = b0 + lane;
+    uint32_t cnt = 0, len = 0, t = 0, key = 0, nc = 0, nqc = 0, alt = 0;
+    const uint32_t* rp = nullptr;
+    if (b < n_buckets) cnt = p.boffs[b + 1] - p.boffs[b];
+    if (cnt) {
+      t = b >> p.sbits; key = b & ((1u << p.sbits) - 1);
+      rp = p.tables[t].row_ptr;
+      len = rp[key + 1] - rp[key];
+      nc = (len + p.cpi - 1) / p.cpi; nqc = (cnt + p.qt - 1) / p.qt;
+      if (!write && p.n_items_alt) alt = ((len + p.cpi_alt - 1) / p.cpi_alt) * ((cnt + p.qt_alt - 1) / p.qt_alt);
     }
-    if (write) {
+    const uint32_t mine = nc * nqc;
+    uint32_t incl = mine;                                    // inclusive prefix sum over the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (!total) continue;
+    uint32_t wbase = 0;
+    if (lane == 0) wbase = atomicAdd(p.n_items, total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    const uint32_t base = wbase + incl - mine;
+    if (!write) {
+      if (__any_sync(0xffffffffu, len >= (1u << 26))) {      // giant buckets (degenerate data): 32-bit warp sums could wrap
+        if (len) atomicAdd(p.bucket_codes, (unsigned long long)len);
+      } else {
+        const uint32_t wl = __reduce_add_sync(0xffffffffu, len);
+        if (lane == 0) atomicAdd(p.bucket_codes, (unsigned long long)wl);
+      }
+      if (p.n_items_alt) {
+        const uint32_t wa = __reduce_add_sync(0xffffffffu, alt);
+        if (lane == 0 && wa) atomicAdd(p.n_items_alt, wa);
+      }
+    } else if (cnt) {
       const uint32_t start = rp[key];
       for (uint32_t c = 0; c < nc; ++c)
         for (uint32_t qc = 0; qc < nqc; ++qc) {
