@@ -19,9 +19,14 @@ for _ in range(3):
         ix.search_linear(q, 100)
     ns = ix.get_param("last_kernel_ns")
 if mode == "mih":
-    print(mode, "n", n, "B", B, "kernel_ms", ns / 1e6, sys.argv[4:])
+    import time
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ix.search_mih(q, 100, with_stats=False)
+    dt = (time.perf_counter() - t0) / 3
+    print(mode, "n", n, "B", B, "kernel_ms", ns / 1e6, "e2e_ms", dt * 1e3, "steps_ms", [ix.get_param("mih.step_ns.%d" % i) / 1e6 for i in range(ix.get_param("mih.last_levels"))], sys.argv[4:])
 else:
     print(mode, "n", n, "B", B, "kernel_ms", ns / 1e6, "pairs/s %.3e" % (n * B / (ns * 1e-9)), "GB/s %.1f" % (n * 8 / ns),
           "grid", ix.get_param("scan.last_grid"), "qt", ix.get_param("scan.last_qt"), "occ", ix.get_param("scan.last_occ"), "stages", ix.get_param("scan.last_stages"),
           "smem", ix.get_param("scan.last_smem"), sys.argv[4:])
-print("tc units", ix.get_param("tc.last_units"), "flagged", ix.get_param("tc.last_flagged"), "hits", ix.get_param("tc.last_hits"))
+

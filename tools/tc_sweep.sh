@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_bmih.py tests/test_gpu_tc.py tests/test_gpu_sharded.py -x -q -m gpu 2>&1 | tail -3
+timeout 200 python tools/scan_probe.py mih 1000000000 4096 2>&1 | head -2
 VC_BENCH_Q=4096 VC_BENCH_SKIP_CPU=1 VC_BENCH_SKIP_BIG_SCAN=1 timeout 300 python bench.py --steps 4 --warmup 3 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.readline())

@@ -122,6 +122,8 @@ struct vc_index {
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
+  uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
+  int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(4096, 16 k))
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
   // tensor-core verify kernel (tcverify.cuh): 0 never (default: measured slower than the POPC kernels),
   // 1 whenever legal, -1 by size (scan: >= scan.tc_min queries; MIH: steps with >= mih.tc_ratio queries per code)
@@ -423,7 +425,7 @@ int vc_index_build(vc_index* ix) {
   if (!ix->d_codes) { int rc = reserve_codes(ix, 1); if (rc) return rc; }
   int rc = ix->W == 1 ? build_tables_impl<1>(ix) : ix->W == 2 ? build_tables_impl<2>(ix) : build_tables_impl<4>(ix);
   if (rc) { free_tables(ix); return rc; }
-  ix->built = true;
+  ix->built = true; ix->max_bucket_len = 0;
   return VC_OK;
 }
 
@@ -530,7 +532,7 @@ int vc_index_load(int device, const char* path, vc_index** out) {
     if (e != cudaSuccess) rc = fail(VC_ERR_CUDA, "table descriptors: %s", cudaGetErrorString(e));
   }
   if (rc) { vc_index_destroy(ix); return rc; }
-  ix->built = true;
+  ix->built = true; ix->max_bucket_len = 0;
   *out = ix;
   return VC_OK;
 }
@@ -993,6 +995,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.exec_pairs = (unsigned long long*)(ctr + 12);
   p.scan_mode = 0; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
   p.gglobkey = ix->allreduce_fn ? (uint64_t*)(sb + o_globkey) : nullptr;
+  p.boot_sample = (uint32_t)std::max<int64_t>(0, ix->mih_boot_sample);
   p.tc_stats = (unsigned long long*)(ctr + 16);
   const uint32_t popc_cpi = p.cpi;
   const bool tc_possible = ix->mih_tc != 0;
@@ -1007,6 +1010,15 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   uint32_t* actA = (uint32_t*)(sb + o_actA);
   uint32_t* actB = (uint32_t*)(sb + o_actB);
 
+  if (ix->max_bucket_len == 0) {
+    CU(cudaMemsetAsync(ctr, 0, 4, st));
+    bmih_maxlen_kernel<<<grid_for(n_buckets, 256, ix->num_sms), 256, 0, st>>>(ix->d_tab, m, sbits, ctr);
+    uint32_t mx = 0;
+    CU(cudaMemcpyAsync(&mx, ctr, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ix->max_bucket_len = std::max(mx, 1u);
+    ix->launches++;
+  }
   // ---- start: all queries active, thresholds bootstrapped from a sample of each query's own buckets -------
   CU(cudaMemsetAsync(ctr, 0, 128, st));
   CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));      // histograms count this search's candidates only
@@ -1057,12 +1069,23 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     CU(cudaMemsetAsync(ctr + 5, 0, 4, st));
     const int igrid = grid_for(n_buckets, 256, ix->num_sms);
     p.cpi = popc_cpi; p.qt = kBmihQT;
+    // work items: normally ONE pass into a buffer sized by a bound that needs no device data (every probed bucket gives
+    // <= ceil(longest bucket / cpi) x ceil(its queries / 32) items) - no counting pass, no host round trip; the counting
+    // pass remains for the tensor-core choice and for degenerate tables whose bound would be huge
+    const uint64_t nc_max = ((uint64_t)ix->max_bucket_len + p.cpi - 1) / p.cpi;
+    const uint64_t item_bound = std::max<uint64_t>(1, nc_max) * (total_probes / kBmihQT + std::min<uint64_t>((uint64_t)(t1 - t0) << sbits, total_probes) + 1);
+    const bool single_pass = !tc_possible && item_bound <= (64ull << 20);
+    uint32_t h12[12] = {0};
+    uint32_t n_items = 0;
+    if (single_pass) {
+      if ((rc = ix->b_items.ensure((size_t)item_bound * sizeof(BmihItem)))) return rc;
+    } else {
     bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 0);
-    uint32_t h12[12];
     CU(cudaMemcpyAsync(h12, ctr, 48, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(h_ctr, h12, 16);
-    uint32_t n_items = h_ctr[0];
+    n_items = h_ctr[0];
+    }
     // which verify kernel?  pairs / codes = queries per code of this step: the POPC kernel pays for every pair, the
     // tensor-core kernel a flat >= 91 clocks per 128 codes for up to 64 queries
     bool step_tc = false;
@@ -1089,10 +1112,11 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
         ++ix->last_mih_tc_steps;
       }
     }
-    if ((rc = ix->b_items.ensure(std::max<size_t>(n_items, 1) * sizeof(BmihItem)))) return rc;
+    if (!single_pass && (rc = ix->b_items.ensure(std::max<size_t>(n_items, 1) * sizeof(BmihItem)))) return rc;
     p.items = (BmihItem*)ix->b_items.p;
     CU(cudaMemsetAsync(ctr, 0, 12, st));
     CU(cudaMemsetAsync(ctr + 4, 0, 4, st));
+    p.count_in_write = single_pass ? 1u : 0u;
     bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
     const bool timed = ix->profile && levels < 34;
     if (timed) {
@@ -1112,7 +1136,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       if (ix->allreduce_fn(ix->allreduce_user, xhist, (uint64_t)nq * Cfg::HB, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
     }
     bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
-    ix->launches += 7;
+    ix->launches += single_pass ? 6 : 7;
     CU(cudaGetLastError());
     uint32_t h5[14];
     CU(cudaMemcpyAsync(h5, ctr, 56, cudaMemcpyDeviceToHost, st));
@@ -1125,6 +1149,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       prev_codes = cc; prev_pairs = pp; prev_exec = xx;
     }
     h_ctr[3] = h5[3];
+    if (single_pass) n_items = h5[0];
     const uint32_t n_likely = h5[4];
     n_active = h5[2];
     std::swap(cur, nxt);
@@ -1279,6 +1304,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.tc")) ix->mih_tc = value;
   else if (!strcmp(name, "mih.tc_ratio")) ix->mih_tc_ratio = value;
   else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
+  else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
   else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
