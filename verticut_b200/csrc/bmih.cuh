@@ -210,8 +210,8 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
 // ghist[q][b] holds CUMULATIVE counts: distinct known codes at distance <= b (maintained for b below the
 // threshold only - bins at or above it are never consulted again, since thresholds only fall).
 template <int W>
-__device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
-                                         CodeRegs<W> c, uint32_t* qrec /* shared: query words, then tau */, uint32_t tau_s) {
+__device__ __forceinline__ void bmih_append_impl(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
+                                                 CodeRegs<W> c, uint32_t* qrec /* shared: query words, then tau */, uint32_t tau_s) {
   const BmihParams& p = *pp;
   // first-discoverer test: table t holds this code at substring distance r_own from the query (the radius at
   // which this bucket was probed for this query); it is emitted here only if no other table holds it at a
@@ -245,6 +245,24 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
     atomicMin(&qrec[2 * W], nt);
   }
 }
+template <int W>
+__device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
+                                         CodeRegs<W> c, uint32_t* qrec, uint32_t tau_s) {
+  bmih_append_impl<W>(pp, qid, t, d, j, c, qrec, tau_s);
+}
+
+// The verify kernel's per-warp staging areas live at namespace scope so that its rare path finds the warp's slice by
+// itself, from the staged query's index: a pointer argument would have to be kept (in practice: rebuilt from
+// SR_CgaCtaId, seven instructions per record) inside the distance loop, which has no registers to spare.
+constexpr int kBmihQSMax = 12;                                      // BmihCfg<4>::QS
+__shared__ __align__(16) uint32_t bv_qrec[(kBmihThreads / 32) * kBmihQT * kBmihQSMax];
+__shared__ uint32_t bv_qid[kBmihThreads / 32][kBmihQT];
+template <int W, int QS>
+__device__ __noinline__ void bmih_append_staged(const BmihParams* pp, uint32_t qq, uint32_t t, uint32_t d, uint32_t j, CodeRegs<W> c,
+                                                uint32_t tau_s) {
+  const uint32_t warp = threadIdx.x >> 5;
+  bmih_append_impl<W>(pp, bv_qid[warp][qq], t, d, j, c, bv_qrec + warp * (kBmihQT * QS) + qq * QS, tau_s);
+}
 
 // Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
 // item's queries in its slice of shared memory and streams the item's codes 32 lanes x C codes at a time.
@@ -254,16 +272,15 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
   constexpr int C = Cfg::C, QS = Cfg::QS;
   constexpr int NW = kBmihThreads / 32;
   constexpr uint32_t WSTEP = 32 * C;                       // codes per warp step
-  __shared__ __align__(16) uint32_t s_qrec_all[NW][kBmihQT * QS];
-  __shared__ uint32_t s_qid_all[NW][kBmihQT];
   __shared__ const uint64_t* s_codes[kMaxTables];          // table payload pointers, fetched once
   __shared__ const uint32_t* s_ids[kMaxTables];
   __shared__ uint32_t s_cut_all[NW][kBmihQT];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < p.m) { s_codes[tid] = p.tables[tid].codes; s_ids[tid] = p.tables[tid].ids; }
   __syncthreads();
-  uint32_t* s_qrec = s_qrec_all[warp];
-  uint32_t* s_qid = s_qid_all[warp];
+  static_assert(QS <= kBmihQSMax, "staging area too small");
+  uint32_t* s_qrec = bv_qrec + warp * (kBmihQT * QS);
+  uint32_t* s_qid = bv_qid[warp];
   uint32_t* s_cut = s_cut_all[warp];
   // Codes not found before this step have substring distance >= r + 1 in the tables before t_begin and >= r in the
   // others: distance >= lb.  A query whose k-th best is already AT that distance can only improve by ties with a
@@ -293,24 +310,27 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
     const uint32_t a0 = W == 1 ? (c0 & ~1u) : c0;                      // 16-byte aligned start
     const uint4* src = reinterpret_cast<const uint4*>(s_codes[t] + (size_t)a0 * W);
     const uint32_t u4_end = ((c1 - a0) * W + 1) / 2;                   // 16-byte units of the item
+    const uint32_t u4_last = u4_end - 1;
     CodeRegs<W> code[C];
     auto load_step = [&](uint32_t base) {
       const uint32_t u4_base = (base - a0) * W / 2;
 #pragma unroll
       for (int u = 0; u < U4; ++u) {
-        uint4 v = make_uint4(0, 0, 0, 0);
+        // lanes past the end of the item re-read its last 16 bytes (no predicate, no zero fill): what they find is
+        // dropped by the range test in front of the append
+        uint4 v;
         if constexpr (W == 1) {
-          const uint32_t idx = u4_base + u * 32 + lane;
-          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          const uint32_t idx = min(u4_base + u * 32 + lane, u4_last);
+          v = ld_stream_u4(src + idx);
           code[2 * u].w[0] = v.x; code[2 * u].w[1] = v.y; code[2 * u + 1].w[0] = v.z; code[2 * u + 1].w[1] = v.w;
         } else if constexpr (W == 2) {
-          const uint32_t idx = u4_base + u * 32 + lane;
-          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          const uint32_t idx = min(u4_base + u * 32 + lane, u4_last);
+          v = ld_stream_u4(src + idx);
           code[u].w[0] = v.x; code[u].w[1] = v.y; code[u].w[2] = v.z; code[u].w[3] = v.w;
         } else {
           const int cc = u / 2, h = u % 2;
-          const uint32_t idx = u4_base + 2 * (cc * 32 + lane) + h;
-          if (idx < u4_end) v = ld_stream_u4(src + idx);
+          const uint32_t idx = min(u4_base + 2 * (cc * 32 + lane), u4_last - 1) + h;
+          v = ld_stream_u4(src + idx);
           code[cc].w[4 * h + 0] = v.x; code[cc].w[4 * h + 1] = v.y; code[cc].w[4 * h + 2] = v.z; code[cc].w[4 * h + 3] = v.w;
         }
       }
@@ -397,13 +417,23 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
         if (mn <= tau) {
           uint32_t qq = q;
           asm volatile("" : "+r"(qq));        // keeps the address arithmetic of this rare path out of the loop body
+          // the minimum did not say which code: groups of four are ruled out by their own minimum, then the cheap bound
+          // again per code (one POPC, not two, for the rest)
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            // the cheap bound again first (the minimum above did not say which code): one POPC, not two, for the rest
-            if (!PREFILTER || hamming_lower_bound<W>(code[c].w, cur.qw) <= tau) {
-              const uint32_t d = hamming_exact<W>(code[c].w, cur.qw);
-              const uint32_t j = base + local_of(c);
-              if (d <= tau && j >= c0 && j < c1) bmih_append<W>(&p, s_qid[qq], t, d, j, code[c], s_qrec + qq * QS, tau);
+          for (int g = 0; g < C; g += 4) {
+            if constexpr (PREFILTER && C > 4) {
+              uint32_t gm = hamming_lower_bound<W>(code[g].w, cur.qw);
+#pragma unroll
+              for (int c = g + 1; c < g + 4 && c < C; ++c) gm = min(gm, hamming_lower_bound<W>(code[c].w, cur.qw));
+              if (gm > tau) continue;
+            }
+#pragma unroll
+            for (int c = g; c < g + 4 && c < C; ++c) {
+              if (!PREFILTER || hamming_lower_bound<W>(code[c].w, cur.qw) <= tau) {
+                const uint32_t d = hamming_exact<W>(code[c].w, cur.qw);
+                const uint32_t j = base + local_of(c);
+                if (d <= tau && j >= c0 && j < c1) bmih_append_staged<W, QS>(&p, qq, t, d, j, code[c], tau);
+              }
             }
           }
         }
