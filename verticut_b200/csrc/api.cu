@@ -740,7 +740,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
     p.tc_trace = (long long*)ix->b_trace.p;
   }
   if (use_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
-  else rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &grid);
+  else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &grid);
   if (rc) return rc;
   if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
   bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, ident, nq, xhist);
@@ -1125,7 +1125,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     }
     if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
     else if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
-    else rc = pf ? launch_bmih_verify<W, true, 4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 4>(p, ix->num_sms, st, &verify_grid);
+    else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &verify_grid);
     if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
     first_verify = false;

@@ -26,15 +26,36 @@
 
 namespace vc {
 
-constexpr int kBmihThreads = 256;
+#ifndef VC_BMIH_THREADS
+#define VC_BMIH_THREADS 256
+#endif
+#ifndef VC_U4
+#define VC_U4 4
+#endif
+constexpr int kBmihThreads = VC_BMIH_THREADS;
 constexpr int kBmihQT = 32;          // queries per work item
 constexpr int kBmihCap = 4096;       // candidate-buffer entries per query
-constexpr int kBmihU4 = 4;           // 128-bit loads per thread per step (short-bucket variant)
-constexpr int kPfDist = 4;           // L2 prefetch distance of the verify kernel, in warp steps of 2 KB
+constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (short-bucket variant)
+#ifndef VC_VERIFY_CTAS
+#define VC_VERIFY_CTAS 4   // 64-bit codes: 4 CTAs (32 warps, 64 registers) per SM - the kernel is latency-bound, 15.5 instead of 16.7 ms per search
+#endif
+#ifndef VC_PF_DIST
+#define VC_PF_DIST 4
+#endif
+#ifndef VC_TAU_EVERY
+#define VC_TAU_EVERY 1
+#endif
+#ifndef VC_PAIRS_PER_ITEM
+#define VC_PAIRS_PER_ITEM 0
+#endif
+#ifndef VC_APPEND_OVERLAP
+#define VC_APPEND_OVERLAP 0
+#endif
+constexpr int kPfDist = VC_PF_DIST;  // L2 prefetch distance of the verify kernel, in warp steps of 2 KB
 
 template <int W, int U4 = kBmihU4> struct BmihCfg {
   static constexpr int C = 2 * U4 / W;                      // codes per thread per step (U4 = 4: 8 / 4 / 2)
-  static constexpr int STEP = kBmihThreads * C;             // codes per CTA step
+  static constexpr int STEP = 2048 / W;                     // unit of the work-item length (16 KB of codes; a multiple of every warp step)
   static constexpr int QS = (2 * W + 1 + 3) / 4 * 4;        // u32 per staged query: words, tau, pad
   static constexpr int HB = 64 * W + 32;
 };
@@ -229,15 +250,26 @@ __device__ __forceinline__ void bmih_append_impl(const BmihParams* pp, uint32_t 
   }
   const uint64_t key = pack_key(d, p.scan_mode ? p.first_id + j * p.id_stride : p.tables[t].ids[j]);
   if (key >= __ldcg(&p.gtaukey[qid])) return;
-  const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
-  if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
-  else atomicOr(&p.gflag[qid], 1u);
   constexpr int HB = BmihCfg<W>::HB;
   uint32_t* gc = p.ghist + (size_t)qid * HB;
   const uint32_t lim = min(tau_s, (uint32_t)(64 * W + 1));      // bins d .. lim-1 count this code
+#if VC_APPEND_OVERLAP
+  // the two atomics whose results are needed travel together (one L2 round trip instead of two)
+  const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
+  uint32_t old = 0;
+  if (d < lim) old = atomicAdd(&gc[lim - 1], 1u);
+  if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
+  else atomicOr(&p.gflag[qid], 1u);
+  if (d >= lim) return;
+  for (uint32_t b0 = d; b0 + 1 < lim; ++b0) atomicAdd(&gc[b0], 1u);              // fire and forget
+#else
+  const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
+  if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
+  else atomicOr(&p.gflag[qid], 1u);
   if (d >= lim) return;
   for (uint32_t b0 = d; b0 + 1 < lim; ++b0) atomicAdd(&gc[b0], 1u);              // fire and forget
   const uint32_t old = atomicAdd(&gc[lim - 1], 1u);
+#endif
   if (old + 1 >= p.k) {                                        // k codes are now strictly inside the threshold
     uint32_t nt = lim - 1;
     while (nt > 0 && __ldcg(&gc[nt - 1]) >= p.k) --nt;
@@ -267,7 +299,7 @@ __device__ __noinline__ void bmih_append_staged(const BmihParams* pp, uint32_t q
 // Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
 // item's queries in its slice of shared memory and streams the item's codes 32 lanes x C codes at a time.
 template <int W, bool PREFILTER, int U4>
-__global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
+__global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY_CTAS : 3)) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
   using Cfg = BmihCfg<W, U4>;
   constexpr int C = Cfg::C, QS = Cfg::QS;
   constexpr int NW = kBmihThreads / 32;
@@ -363,6 +395,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
     s_cut[lane] = my_cut;
     const bool use_cut = __any_sync(0xffffffffu, my_cut != 0xFFFFFFFFu);
     uint32_t qlive = qn;                               // staged queries still interested in the rest of the item
+    if (VC_PAIRS_PER_ITEM && !use_cut) my_pairs += (unsigned long long)(c1 - c0) * qn;   // no query leaves early: counted once
     __syncwarp();
     for (uint32_t base = a0; base < c1; base += WSTEP) {
       if (use_cut) {
@@ -394,12 +427,13 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
         const uint32_t ahead = (base - a0 + kPfDist * WSTEP) * W / 2;
         if (lane < 16 && ahead + lane * 8 < u4_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ahead + lane * 8));
       }
-      my_pairs += (unsigned long long)(min(c1, base + WSTEP) - max(base, c0)) * qlive;
+      if (!VC_PAIRS_PER_ITEM || use_cut) my_pairs += (unsigned long long)(min(c1, base + WSTEP) - max(base, c0)) * qlive;
       // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
       // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
       // of the codes down the slow path.  The load is issued here and consumed after this step's math.
       uint32_t fresh_tau = kInfDist;
-      if (lane < qlive) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
+      const bool refresh = VC_TAU_EVERY == 1 || (((base - a0) / WSTEP) % VC_TAU_EVERY) == VC_TAU_EVERY - 1;
+      if (refresh && lane < qlive) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
       // one staged query against this thread's C codes: the minimum of the (lower-bound) distances decides; the rare
       // hit recomputes per code
       auto test_query = [&](const QRec<W>& cur, uint32_t q) {
@@ -449,9 +483,11 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : 3) bmih_verify_kern
           test_query(rb, q + 1);
         }
       }
-      __syncwarp();
-      if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
-      __syncwarp();
+      if (refresh) {
+        __syncwarp();
+        if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
+        __syncwarp();
+      }
     }
   }
   if (lane == 0 && p.exec_pairs && my_pairs) atomicAdd(p.exec_pairs, my_pairs);
