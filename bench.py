@@ -27,6 +27,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line: NCCL's own messages (NCCL_DEBUG=VERSION/INFO print there by default) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
