@@ -27,8 +27,10 @@ import time
 
 import numpy as np
 
-# stdout carries exactly ONE JSON line: NCCL's own messages (NCCL_DEBUG=VERSION/INFO print there by default) go to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line: whatever native libraries write to file descriptor 1 (NCCL_DEBUG=VERSION/INFO print
+# "NCCL version ..." there) is sent to stderr, the JSON line goes to a private copy of the original stdout
+RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -134,7 +136,7 @@ def reference_arm(args, n_total, world, rank):
                                    % (sample_n, nq, cores)},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def main():
@@ -397,7 +399,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "integer_pipe": integer_pipe, "cpu_baseline": cpu_baseline,
             "parity_selfcheck": "mih == linear scan on 8 queries: %s" % parity_ok, "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     ix.close()
     if world > 1:
         dist.destroy_process_group()
