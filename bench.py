@@ -29,8 +29,14 @@ import numpy as np
 
 # stdout carries exactly ONE JSON line: whatever native libraries write to file descriptor 1 (NCCL_DEBUG=VERSION/INFO print
 # "NCCL version ..." there) is sent to stderr, the JSON line goes to a private copy of the original stdout
-RESULT_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+RESULT_OUT = sys.stdout
+
+
+def _private_stdout():
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -406,4 +412,5 @@ def main():
 
 
 if __name__ == "__main__":
+    _private_stdout()
     main()
