@@ -197,7 +197,11 @@ class image_search_server {
   void worker() {
     while (!stop_) {
       const int fd = ::accept(lfd_, 0, 0);
-      if (fd < 0) { if (errno == EINTR) continue; break; }
+      if (fd < 0) {
+        if (stop_ || errno == EBADF || errno == EINVAL || errno == ENOTSOCK) break;      // the listening socket is gone
+        if (errno != EINTR && errno != ECONNABORTED) usleep(10000);                       // out of descriptors / memory: try again
+        continue;
+      }
       int one = 1;
       ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof one);
       { std::lock_guard<std::mutex> g(mu_); conns_.insert(fd); }
