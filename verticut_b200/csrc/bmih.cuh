@@ -39,6 +39,9 @@ constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (s
 #ifndef VC_VERIFY_CTAS
 #define VC_VERIFY_CTAS 4   // 64-bit codes: 4 CTAs (32 warps, 64 registers) per SM - the kernel is latency-bound, 15.5 instead of 16.7 ms per search
 #endif
+#ifndef VC_VERIFY_CTAS_W2
+#define VC_VERIFY_CTAS_W2 3   // 128- and 256-bit codes: not re-measured at 4 CTAs per SM yet
+#endif
 #ifndef VC_PF_DIST
 #define VC_PF_DIST 4
 #endif
@@ -299,7 +302,7 @@ __device__ __noinline__ void bmih_append_staged(const BmihParams* pp, uint32_t q
 // Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
 // item's queries in its slice of shared memory and streams the item's codes 32 lanes x C codes at a time.
 template <int W, bool PREFILTER, int U4>
-__global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY_CTAS : 3)) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
+__global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY_CTAS : VC_VERIFY_CTAS_W2)) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
   using Cfg = BmihCfg<W, U4>;
   constexpr int C = Cfg::C, QS = Cfg::QS;
   constexpr int NW = kBmihThreads / 32;
