@@ -42,6 +42,9 @@ constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (s
 #ifndef VC_VERIFY_CTAS_W2
 #define VC_VERIFY_CTAS_W2 3   // 128- and 256-bit codes: not re-measured at 4 CTAs per SM yet
 #endif
+#ifndef VC_KEY_SUBST
+#define VC_KEY_SUBST 0       // experimental (not measured yet): bucket key substituted into the staged queries, see bmih_verify_kernel
+#endif
 #ifndef VC_PF_DIST
 #define VC_PF_DIST 4
 #endif
@@ -235,15 +238,18 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
 // threshold only - bins at or above it are never consulted again, since thresholds only fall).
 template <int W>
 __device__ __forceinline__ void bmih_append_impl(const BmihParams* pp, uint32_t qid, uint32_t t, uint32_t d, uint32_t j,
-                                                 CodeRegs<W> c, uint32_t* qrec /* shared: query words, then tau */, uint32_t tau_s) {
+                                                 CodeRegs<W> c, uint32_t* qrec /* shared: query words, then tau */, uint32_t tau_s,
+                                                 const uint32_t* qorig = nullptr /* the query's own words when the staged ones were altered */,
+                                                 uint32_t r_sub = 0 /* what the staged threshold is short of the real one */) {
   const BmihParams& p = *pp;
+  const uint32_t* qo = qorig ? qorig : qrec;
   // first-discoverer test: table t holds this code at substring distance r_own from the query (the radius at
   // which this bucket was probed for this query); it is emitted here only if no other table holds it at a
   // smaller substring distance, or at the same one with a lower table id
   if (!p.scan_mode) {
     uint32_t x[2 * W];
 #pragma unroll
-    for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qrec[i];
+    for (int i = 0; i < 2 * W; ++i) x[i] = c.w[i] ^ qo[i];
     const uint32_t r_own = __popc(substring<W>(x, t, p.sbits));
     for (uint32_t t2 = 0; t2 < p.m; ++t2) {
       if (t2 == t) continue;
@@ -277,7 +283,7 @@ __device__ __forceinline__ void bmih_append_impl(const BmihParams* pp, uint32_t 
     uint32_t nt = lim - 1;
     while (nt > 0 && __ldcg(&gc[nt - 1]) >= p.k) --nt;
     atomicMin(&p.gtau[qid], nt);
-    atomicMin(&qrec[2 * W], nt);
+    atomicMin(&qrec[2 * W], nt >= r_sub ? nt - r_sub : 0u);
   }
 }
 template <int W>
@@ -296,7 +302,15 @@ template <int W, int QS>
 __device__ __noinline__ void bmih_append_staged(const BmihParams* pp, uint32_t qq, uint32_t t, uint32_t d, uint32_t j, CodeRegs<W> c,
                                                 uint32_t tau_s) {
   const uint32_t warp = threadIdx.x >> 5;
+#if VC_KEY_SUBST
+  // d and tau_s are relative to the staged record: the substring of table t is not part of them (bmih_verify_kernel)
+  uint32_t* rec = bv_qrec + warp * (kBmihQT * QS) + qq * QS;
+  const uint32_t qid = bv_qid[warp][qq];
+  const uint32_t r_sub = pp->scan_mode ? 0u : rec[2 * W + 1];
+  bmih_append_impl<W>(pp, qid, t, d + r_sub, j, c, rec, tau_s + r_sub, pp->queries + (size_t)qid * 2 * W, r_sub);
+#else
   bmih_append_impl<W>(pp, bv_qid[warp][qq], t, d, j, c, bv_qrec + warp * (kBmihQT * QS) + qq * QS, tau_s);
+#endif
 }
 
 // Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
@@ -390,6 +404,30 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       if (w == 0) s_qid[i] = qid;
       s_qrec[e] = w < 2 * W ? p.queries[(size_t)qid * 2 * W + w] : (w == 2 * W ? __ldcg(&p.gtau[qid]) : 0u);
     }
+#if VC_KEY_SUBST
+    // Every code of the item has the bucket's key as its substring t, so that substring adds the same r_own = popc(query
+    // substring ^ key) to every distance.  With the key written into the staged query the XOR is zero there: the one-POPC lower
+    // bound no longer loses those 16 bits to the OR with their partner substring, and is tested against tau - r_own (a sharper
+    // filter at no cost per test: ~4 x fewer records on the slow path at radius 2).  The slow path adds r_own back and takes
+    // the query's own words for the first-discoverer test; a threshold below r_own is clamped to 0, which can only let codes
+    // through that the append path then handles with their true distance.
+    static_assert(QS >= 2 * W + 2, "no spare word in the staged record");
+    if (!p.scan_mode) {
+      __syncwarp();
+      if (lane < qn) {
+        uint32_t* rec = s_qrec + lane * QS;
+        const uint32_t key = substring<W>(reinterpret_cast<const uint32_t*>(s_codes[t] + (size_t)c0 * W), t, p.sbits);
+        const uint32_t off = t * p.sbits, wi = off >> 5, sh = off & 31;
+        const uint32_t mask = (p.sbits == 32 ? 0xFFFFFFFFu : ((1u << p.sbits) - 1u)) << sh;
+        const uint32_t qw = rec[wi];
+        const uint32_t r_own = __popc((qw ^ (key << sh)) & mask);
+        rec[wi] = (qw & ~mask) | (key << sh);
+        const uint32_t tau0 = rec[2 * W];
+        rec[2 * W] = tau0 >= r_own ? tau0 - r_own : 0u;
+        rec[2 * W + 1] = r_own;
+      }
+    }
+#endif
     uint32_t my_cut = 0xFFFFFFFFu;
     if (!p.scan_mode && lane < qn) {
       const uint64_t tk = __ldcg(&p.gtaukey[p.qlist[qbeg + lane]]);
@@ -488,7 +526,15 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       }
       if (refresh) {
         __syncwarp();
+#if VC_KEY_SUBST
+        if (lane < qlive) {
+          const uint32_t r_own = s_qrec[lane * QS + 2 * W + 1];
+          const uint32_t ft = fresh_tau >= r_own ? fresh_tau - r_own : 0u;
+          if (ft < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = ft;
+        }
+#else
         if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
+#endif
         __syncwarp();
       }
     }
