@@ -24,15 +24,22 @@ def raw(rep):
     return rows[0], rows[1], rows[2:]
 
 
-def source_top(rep, n=12):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+def source_top(rep, launch, n=12):
+    """Hottest SASS instructions of launch number `launch` of the report (stall samples per instruction address)."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(launch), "--launch-count", "1"],
+                         capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hi = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r]
     if not hi:
         return []
     hdr = rows[hi[0]]
-    isrc, ismp = hdr.index("Source"), hdr.index("# Samples")
-    data = [(int(r[ismp]), r[isrc].strip()) for r in rows[hi[0] + 1:] if len(r) > ismp and r[ismp].isdigit()]
+    isrc, ismp, iadr = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Address")
+    end = hi[1] - 1 if len(hi) > 1 else len(rows)          # the SASS view; a second (source-line) view may follow
+    seen, data = set(), []
+    for r in rows[hi[0] + 1:end]:
+        if len(r) > ismp and r[ismp].isdigit() and r[iadr] not in seen:
+            seen.add(r[iadr])
+            data.append((int(r[ismp]), r[isrc].strip()))
     tot = sum(s for s, _ in data) or 1
     return [(s, 100.0 * s / tot, src) for s, src in sorted(data, reverse=True)[:n]]
 
@@ -42,7 +49,7 @@ def main():
     md = ["# ncu summaries (`ncu --set full --clock-control none`, one launch each)\n"]
     for rep in reps:
         hdr, units, launches = raw(rep)
-        for vals in launches:
+        for li, vals in enumerate(launches):
             d = dict(zip(hdr, vals))
             u = dict(zip(hdr, units))
             md.append("## %s\n" % rep.split("/")[-1])
@@ -51,11 +58,17 @@ def main():
             for k in KEYS:
                 if k in d:
                     md.append("| %s | %s | %s |" % (k, d[k], u.get(k, "")))
-            stalls = sorted(((float(d[h]), h) for h in hdr if "issue_stalled" in h and h.endswith("per_warp_active.pct") and d[h]),
-                            reverse=True)[:6]
-            md.append("\ntop warp stall reasons (% of active warps): " +
-                      ", ".join("%s %.1f" % (h.split("issue_stalled_")[1].split("_per_warp")[0], v) for v, h in stalls))
-            top = source_top(rep)
+            stalls = []
+            for h in hdr:
+                if "pcsamp_warps_issue_stalled_" in h and not h.endswith("_not_issued") and d[h]:
+                    try:
+                        stalls.append((float(d[h].replace(",", "")), h.split("issue_stalled_")[1]))
+                    except ValueError:
+                        pass
+            tot_s = sum(v for v, _ in stalls) or 1.0
+            stalls = sorted(stalls, reverse=True)[:7]
+            md.append("\ntop warp stall reasons (% of the stall samples): " + ", ".join("%s %.1f" % (h, 100.0 * v / tot_s) for v, h in stalls))
+            top = source_top(rep, li)
             if top:
                 md.append("\nhottest SASS instructions (stall samples):\n")
                 md.append("| samples | % | instruction |\n|---|---|---|")
