@@ -60,7 +60,7 @@ def measured_peaks():
 class ClockSampler:
     """SM clock, power and throttle reasons of one GPU sampled through NVML while the timed region runs."""
 
-    def __init__(self, gpu_index, period_s=0.01):   # a timed step is ~16 ms: several samples per step
+    def __init__(self, gpu_index, period_s=0.05):   # a few samples per timed region (NVML queries can hold up launches: not more often)
         self.gpu, self.period = gpu_index, period_s
         self.samples, self.reasons = [], set()
         self._stop = threading.Event()
