@@ -163,6 +163,14 @@ int vc_merge_topk(int device, const uint64_t* lists, uint32_t n_lists, uint32_t 
 typedef int (*vc_allreduce_fn)(void* user, uint32_t* d_words, uint64_t n_words, void* stream);
 int vc_index_set_allreduce(vc_index* ix, vc_allreduce_fn fn, void* user);
 
+/* A ready-made vc_allreduce_fn for hosts that hold an NCCL communicator: `user` points to a vc_nccl_hook with the address of
+ * ncclAllReduce (the library does not link NCCL) and the communicator; the hook issues
+ * ncclAllReduce(d_words, d_words, n_words, ncclUint32, ncclSum, comm, stream) and returns 0 on ncclSuccess.  With it the
+ * per-step exchanges of the id-sharded search are enqueued from C, without a detour through the host language
+ *   vc_index_set_allreduce(ix, vc_nccl_allreduce_hook, &hook);      (the hook struct must outlive its use) */
+typedef struct vc_nccl_hook { void* nccl_allreduce; void* comm; } vc_nccl_hook;
+int vc_nccl_allreduce_hook(void* user, uint32_t* d_words, uint64_t n_words, void* stream);
+
 /* Knobs and counters (integers).  Unknown names return VC_ERR_ARG.
  *   "id_stride"   id of the j-th code added = first_id + j * id_stride (default 1; G for one of G interleaved shards;
  *                 must be set before codes are added; stored by vc_index_save)

@@ -50,3 +50,25 @@ def test_synth_generator_matches_oracle(oracle):
     from verticut_b200 import capi
     for seed, idx, w in [(12345, 0, 0), (12345, 999_999_999, 0), (7, 123456, 3), (67890, 5, 1)]:
         assert capi.synth_word(seed, idx, w) == oracle.lib().vo_synth_word(seed, idx, w)
+
+
+def test_nccl_hook_marshals_an_in_place_uint32_sum():
+    """vc_nccl_allreduce_hook (include/verticut_gpu.h) against a stand-in for ncclAllReduce: in place, count = words,
+    ncclUint32 (3), ncclSum (0), communicator and stream passed through; a non-zero ncclResult_t is an error."""
+    import ctypes as C
+    from verticut_b200 import capi
+    L = capi.lib()
+    seen = {}
+    FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p)
+
+    def fake(send, recv, count, dtype, op, comm, stream):
+        seen.update(send=send, recv=recv, count=count, dtype=dtype, op=op, comm=comm, stream=stream)
+        return seen.get("rc", 0)
+    cb = FN(fake)
+    hook = capi.NcclHook(C.cast(cb, C.c_void_p), C.c_void_p(0xC0FFEE))
+    user = C.cast(C.pointer(hook), C.c_void_p)
+    assert L.vc_nccl_allreduce_hook(user, C.c_void_p(0x7000), 12345, C.c_void_p(0x55)) == 0
+    assert seen == dict(send=0x7000, recv=0x7000, count=12345, dtype=3, op=0, comm=0xC0FFEE, stream=0x55)
+    seen["rc"] = 5
+    assert L.vc_nccl_allreduce_hook(user, C.c_void_p(0x7000), 1, None) != 0 and b"ncclAllReduce" in L.vc_last_error()
+    assert L.vc_nccl_allreduce_hook(None, C.c_void_p(0x7000), 1, None) != 0

@@ -26,6 +26,7 @@ EXPORTS = [
     "vc_bucket_get", "vc_code_get", "vc_occupancy_bitmap_get", "vc_search_linear", "vc_search_mih",
     "vc_search_linear_dev", "vc_search_mih_dev", "vc_merge_topk_dev", "vc_merge_topk",
     "vc_index_set_param", "vc_index_get_param", "vc_index_set_allreduce", "vc_index_save", "vc_index_load",
+    "vc_nccl_allreduce_hook",
 ]
 
 
@@ -42,6 +43,10 @@ class QueryStats(C.Structure):
 
 STATS_DTYPE = np.dtype([("radius", np.uint32), ("n_results", np.uint32), ("probes", np.uint64),
                         ("occupancy_tests", np.uint64), ("candidates", np.uint64), ("unique", np.uint64)])
+
+
+class NcclHook(C.Structure):          # vc_nccl_hook
+    _fields_ = [("nccl_allreduce", C.c_void_p), ("comm", C.c_void_p)]
 
 
 class IndexInfo(C.Structure):
@@ -89,6 +94,7 @@ def lib():
     L.vc_merge_topk_dev.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp]
     L.vc_merge_topk.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.vc_index_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    L.vc_nccl_allreduce_hook.argtypes = [vp, vp, C.c_uint64, vp]
     L.vc_index_set_param.argtypes = [vp, C.c_char_p, C.c_int64]
     L.vc_index_get_param.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     _lib = L
@@ -185,6 +191,14 @@ class Index:
 
         self._allreduce_cb = ALLREDUCE_FN(tramp)      # keep the trampoline alive as long as the index
         check(lib().vc_index_set_allreduce(self.h, self._allreduce_cb, None))
+
+    def set_allreduce_nccl(self, nccl_allreduce_addr, comm):
+        """The per-step exchanges go straight from the library to ncclAllReduce (vc_nccl_allreduce_hook): address of
+        ncclAllReduce in the loaded NCCL library and an ncclComm_t of this rank, both as integers."""
+        self._nccl_hook = NcclHook(C.c_void_p(nccl_allreduce_addr), C.c_void_p(comm))      # must outlive the index's use of it
+        self._allreduce_cb = None
+        fn = C.cast(lib().vc_nccl_allreduce_hook, ALLREDUCE_FN)
+        check(lib().vc_index_set_allreduce(self.h, fn, C.cast(C.pointer(self._nccl_hook), C.c_void_p)))
 
     def set_param(self, name, value):
         check(lib().vc_index_set_param(self.h, name.encode(), int(value)))

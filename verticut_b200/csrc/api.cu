@@ -1285,6 +1285,15 @@ int vc_index_set_allreduce(vc_index* ix, vc_allreduce_fn fn, void* user) {
   return VC_OK;
 }
 
+int vc_nccl_allreduce_hook(void* user, uint32_t* d_words, uint64_t n_words, void* stream) {
+  const vc_nccl_hook* h = (const vc_nccl_hook*)user;
+  if (!h || !h->nccl_allreduce || !h->comm) return fail(VC_ERR_ARG, "vc_nccl_allreduce_hook: no NCCL entry point or communicator");
+  // ncclResult_t ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); ncclUint32 = 3, ncclSum = 0
+  typedef int (*nccl_allreduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  const int rc = ((nccl_allreduce_t)h->nccl_allreduce)(d_words, d_words, (size_t)n_words, 3, 0, h->comm, (cudaStream_t)stream);
+  return rc == 0 ? VC_OK : fail(VC_ERR_STATE, "ncclAllReduce failed (ncclResult_t %d)", rc);
+}
+
 int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   if (!ix || !name) return fail(VC_ERR_ARG, "null argument");
   if (!strcmp(name, "scan.prefilter")) ix->scan_prefilter = value;

@@ -17,6 +17,8 @@ flag once per radius step (src/mpi_coordinator.cc:26-69, src/search_worker.cc:17
 torch.distributed is plumbing here (process group, the all-gather, device buffers); searching and
 merging are the library's CUDA kernels, called through the C ABI with raw device pointers.
 """
+import os
+
 import numpy as np
 
 from . import capi
@@ -65,6 +67,36 @@ class ShardedSearcher:
         self._views = {}
         if self.world > 1 and global_threshold and hasattr(index, "set_allreduce"):
             index.set_allreduce(self._allreduce_words)
+            if os.environ.get("VC_NCCL_DIRECT") == "1" and hasattr(index, "set_allreduce_nccl"):
+                self._nccl_direct()
+
+    def _nccl_direct(self):
+        """EXPERIMENTAL (VC_NCCL_DIRECT=1; written without a GPU at hand, not measured yet): the library's per-step
+        exchanges call ncclAllReduce themselves (vc_nccl_allreduce_hook) on a communicator of their own instead of coming
+        back to Python for torch.distributed.all_reduce - half a dozen callbacks per search, which at 8 GPUs is a tenth of
+        the batch time.  torch.distributed stays the plumbing: it carries the ncclUniqueId to the other ranks."""
+        import ctypes as C
+        t, dist = self.torch, self.dist
+        nccl = C.CDLL("libnccl.so.2")                     # by soname: the copy torch has already loaded
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_byte * 128)]
+
+        uid = UniqueId()
+        if self.rank == 0 and nccl.ncclGetUniqueId(C.byref(uid)) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+        dev = t.device("cuda", self.index.device)
+        buf = t.tensor(list(bytes(uid)), dtype=t.uint8, device=dev)
+        dist.broadcast(buf, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        C.memmove(C.byref(uid), bytes(buf.cpu().tolist()), 128)
+        comm = C.c_void_p()
+        nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        with t.cuda.device(dev):
+            rc = nccl.ncclCommInitRank(C.byref(comm), self.world, uid, self.rank)
+        if rc != 0:
+            raise RuntimeError("ncclCommInitRank failed (ncclResult_t %d)" % rc)
+        self._nccl = (nccl, comm)                          # keep the library handle and the communicator alive
+        self.index.set_allreduce_nccl(C.cast(nccl.ncclAllReduce, C.c_void_p).value, comm.value)
 
     def _allreduce_words(self, ptr, n_words, stream):
         """Sum n_words int32 words at device address ptr over the ranks (NCCL), ordered after `stream`."""
