@@ -9,7 +9,7 @@
 //
 // The reference's server forks `ssh worker ... mpirun` per query and parses the worker's "id : dist" lines
 // (:58-100); this one answers from a `service` object in the same process (the GPU-resident index behind the
-// in-process image_search_client, see image_server_main.cc).  msgpack-rpc / mpio are not available here, so the
+// in-process image_search_client, see rpc_server_main.cc).  msgpack-rpc / mpio are not available here, so the
 // transport is hand-written on POSIX sockets: worker threads share one listening socket (the reference runs
 // `instance.run(n_threads)` with 10 threads, src/image_server_main.cc:13,90), one connection per thread at a time.
 //

@@ -35,13 +35,15 @@ static struct option long_options[] = {
     {0, 0, 0, 0}};
 
 static void usage() {
-  printf("Usage : \n");
-  printf("--config_path -c : The device list of the GPU proxy (one CUDA ordinal per line).\n");
-  printf("--port -p : The port number the server listens to.\n");
-  printf("--ip -i : The ip address the server listens to.\n");
-  printf("--nthreads -n : The maximum number of requests the server can process simultaneously.\n");
-  printf("--index -x : A built index (build-tables -o).  Or: --binary_file -f, --binary_bits -b, --ntables -t, --image_total -N.\n");
-  exit(-1);
+  fprintf(stderr,
+          "image-search-server: msgpack-rpc query server in front of a GPU-resident index\n"
+          "  -p, --port <n>          TCP port (default 9191; 0 = any free port, printed as \"port <n>\")\n"
+          "  -i, --ip <addr>         address to bind (default 0.0.0.0)\n"
+          "  -n, --nthreads <n>      connections served at the same time (default 10)\n"
+          "  -c, --config_path <f>   device list of the GPU proxy, one CUDA ordinal per line (default: device 0)\n"
+          "  -x, --index <f>         index written by build-tables -o, or instead:\n"
+          "  -f, --binary_file <f>   raw code file, with -b/--binary_bits, -t/--ntables, -N/--image_total\n");
+  exit(2);
 }
 
 struct gpu_service : vcrpc::service {
