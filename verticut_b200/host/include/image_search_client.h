@@ -7,7 +7,7 @@
 // reference that path is dead (src/distributed_image_search.cc:116).
 // Two kinds of connection: in-process (constructed from the proxy that holds the tables), or - the reference's own
 // constructor, image_search_client(ip, port) - msgpack-rpc over TCP to an image-search-server (image_search_rpc.h,
-// src/image_server_main.cc), whose wire format is the reference's.
+// host/src/rpc_server_main.cc), whose wire format is the reference's.
 #ifndef VERTICUT_B200_IMAGE_SEARCH_CLIENT_H
 #define VERTICUT_B200_IMAGE_SEARCH_CLIENT_H
 
