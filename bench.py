@@ -293,12 +293,13 @@ def main():
                 meas_s += sn
             roofline["combined"] = {"what": "sum over search steps of max(HBM time, POPC time) / measured verify-kernel time",
                                     "bound_ms": bound_s * 1e3, "measured_ms": meas_s * 1e3, "frac": bound_s / meas_s, "steps": steps}
-            tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-            if os.path.exists(tpath):
-                tj = json.load(open(tpath))
+            import glob
+            tpaths = sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")))      # the newest round's capture
+            if tpaths:
+                tj = json.load(open(tpaths[-1]))
                 if tj["config"] == {"n_codes": n_total, "batch": Q, "k": K_NN, "n_gpus": world}:
                     roofline["traffic"] = tj["traffic_bytes_per_search"]
-                    roofline["traffic_source"] = "profiles/traffic_r01.json (ncu --set full, all verify launches of one search)"
+                    roofline["traffic_source"] = "profiles/%s (ncu --set full, all verify launches of one search)" % os.path.basename(tpaths[-1])
         sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
         n_sms = ix.get_param("num_sms")
         pairs_s = (exec_pairs if batched else cands) / k_s
