@@ -177,6 +177,7 @@ class Index:
         place (see vc_index_set_allreduce); fn = None removes the hook."""
         if fn is None:
             self._allreduce_cb = None
+            self._nccl_hook = None
             check(lib().vc_index_set_allreduce(self.h, C.cast(None, ALLREDUCE_FN), None))
             return
 
