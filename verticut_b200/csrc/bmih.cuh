@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         }
       }
       if (base != a0) load_step(base);
-      {
+      if constexpr (kPfDist > 0) {
         // the codes kPfDist steps ahead on their way into L2 (a warp step is 2 KB = 16 lines; no registers needed)
         const uint32_t ahead = (base - a0 + kPfDist * WSTEP) * W / 2;
         if (lane < 16 && ahead + lane * 8 < u4_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ahead + lane * 8));
