@@ -31,8 +31,7 @@ def _data(n, bits, nq, seed=12345):
     (6000, 64, 4, 3, 5, True),
     (40, 64, 4, 100, 3, False),       # fewer codes than k: the loop runs to r = s (search_worker.cc:170)
     (5000, 64, 8, 10, 4, False),      # s = 8
-    # no 256-bit case: the reference's own build reads every record into `char code[17]` (src/build_hash_tables.cc:41) and
-    # overflows beyond 128 bits ("buffer overflow detected" under _FORTIFY_SOURCE) - config C5 is out of its reach
+    # 256-bit codes: test_restatement_reproduces_reference_search_at_256_bits (the reference's own build overflows there)
 ])
 def test_restatement_reproduces_reference_mih_exactly(n, bits, m, k, nq, approx):
     codes, queries = _data(n, bits, nq)
@@ -47,6 +46,24 @@ def test_restatement_reproduces_reference_mih_exactly(n, bits, m, k, nq, approx)
     for q in range(nq):
         assert ost[q]["radius"] == rrad[q]
         assert ost[q]["probes"] == rsub[q].sum()  # n_sub_reads_ (search_worker.cc:245), all ranks
+
+
+@pytest.mark.parametrize("n,bits,m,k,nq,approx", [(2000, 256, 16, 10, 2, False), (2000, 256, 16, 5, 2, True), (3000, 256, 16, 100, 2, False)])
+def test_restatement_reproduces_reference_search_at_256_bits(n, bits, m, k, nq, approx):
+    """Config C5's geometry.  The reference's build cannot take 256-bit codes (`char code[17]`, src/build_hash_tables.cc:41 -
+    the unmodified build aborts with "buffer overflow detected"), its search can: the tables are filled by the driver's own
+    loop (RefMem, oracle/ref_driver.cc) and the unmodified SearchWorker::find runs over them.  With 256-bit codes the
+    hard-coded `top.dist <= radius*4` never fires, so the exact search runs to r = s (src/search_worker.cc:170,204)."""
+    codes, queries = _data(n, bits, nq)
+    rid, rd, rc, rrad, rsub = F.RefMem(codes, m).mih_search(queries, k, approximate=approx)
+    oid, od, oc, ost = R.Index(codes, m).search(queries, k, order=R.ORDER_REFERENCE, stop=R.STOP_REF4, approximate=approx)
+    np.testing.assert_array_equal(oc, rc)
+    np.testing.assert_array_equal(od, rd)
+    np.testing.assert_array_equal(oid, rid)
+    for q in range(nq):
+        assert ost[q]["radius"] == rrad[q] and ost[q]["probes"] == rsub[q].sum()
+    if not approx:
+        assert (rrad == bits // m).all()
 
 
 def test_restatement_reproduces_reference_linear_scan_exactly():
@@ -64,7 +81,7 @@ def test_restatement_reproduces_reference_linear_scan_exactly():
     np.testing.assert_array_equal(md, rd)
 
 
-@pytest.mark.parametrize("bits,m", [(64, 4), (128, 8), (64, 8)])
+@pytest.mark.parametrize("bits,m", [(64, 4), (128, 8), (64, 8), (64, 2), (128, 4)])      # s = 16, 16, 8, 32, 32
 def test_tables_match_reference_build(bits, m):
     n = 5000
     codes, _ = _data(n, bits, 1)
