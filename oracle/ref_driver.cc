@@ -472,6 +472,70 @@ int ref_mem_mih_search(const uint8_t* queries, int nq, int nbytes, int n_tables,
   return 0;
 }
 
+// Fixed-radius search (BASELINE config C5: radii 0 .. max_radius, no stop rule, the k best of what was found).  The reference
+// has no such entry point, but its pieces are reachable from a subclass (the members are protected, search_worker.h:35-63):
+// candidate generation is the reference's own search_R_neighbors / enumerate_entry (probe order, bucket reads, distances)
+// and its gather_vectors (rank-order concatenation); only the master's bookkeeping between them - first-seen-wins
+// de-duplication and the size-k max-heap with strict-less replacement, search_worker.cc:183-197 - is written out again
+// here, without the stop test of :204.
+extern "C++" bool operator<(const SearchWorker::search_result_st& a, const SearchWorker::search_result_st& b);   // src/search_worker.cc:15, the reference's own
+struct FixedRadiusWorker : SearchWorker {
+  FixedRadiusWorker(mpi_coordinator* c, Proxy* p, int total) : SearchWorker(c, p, total) {}
+  std::list<search_result_st> find_fixed(const char* binary_code, size_t nbytes, int knn, int max_radius) {
+    knn_ = knn; knn_found_.clear(); result_.clear();                         // find(), search_worker.cc:67-76
+    n_main_reads_ = 0; n_sub_reads_ = 0; n_local_reads_ = 0;
+    n_local_bytes_ = (int)(nbytes / coord_->get_size());
+    std::string query_code(binary_code, nbytes);
+    std::string local = query_code.substr((size_t)coord_->get_rank() * n_local_bytes_, n_local_bytes_);
+    const uint32_t search_index = binaryToInt(local.c_str(), n_local_bytes_);
+    std::priority_queue<search_result_st> qmax;
+    for (int radius = 0; radius <= max_radius && radius <= n_local_bytes_ * 8; ++radius) {
+      std::vector<uint64_t> cand;
+      search_R_neighbors(query_code, radius, search_index, cand);
+      std::vector<uint64_t> all = coord_->gather_vectors(cand);
+      if (!coord_->is_master()) continue;
+      for (size_t i = 0; i < all.size(); ++i) {
+        const uint32_t id = (uint32_t)(all[i] & 0xffffffffu);
+        if (knn_found_.find((int)id) != knn_found_.end()) continue;
+        knn_found_[(int)id] = 1;
+        search_result_st item; item.image_id = id; item.dist = (uint32_t)(all[i] >> 32);
+        if ((int)qmax.size() < knn_) qmax.push(item);
+        else if (qmax.top().dist > item.dist) { qmax.pop(); qmax.push(item); }
+      }
+    }
+    while (!qmax.empty()) { result_.push_back(qmax.top()); qmax.pop(); }
+    return result_;
+  }
+  uint64_t sub_reads() const { return n_sub_reads_; }
+};
+
+int ref_mem_fixed_radius_search(const uint8_t* queries, int nq, int nbytes, int n_tables, int k, int max_radius, int image_count,
+                                uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, uint64_t* out_sub_reads) {
+  if (nbytes % n_tables != 0) return 1;
+  vc_shim_mpi_set_world(n_tables);
+  std::vector<std::thread> th;
+  for (int r = 0; r < n_tables; ++r) {
+    th.emplace_back([=] {
+      vc_shim_mpi_set_rank(r);
+      mpi_coordinator coord;
+      FixedRadiusWorker worker(&coord, &g_mem, image_count);
+      for (int q = 0; q < nq; ++q) {
+        std::list<SearchWorker::search_result_st> res = worker.find_fixed((const char*)queries + (size_t)q * nbytes, nbytes, k, max_radius);
+        if (out_sub_reads) out_sub_reads[(size_t)q * n_tables + r] = worker.sub_reads();
+        if (r == 0) {
+          uint32_t i = 0;
+          for (auto it = res.begin(); it != res.end(); ++it, ++i) { out_ids[(size_t)q * k + i] = it->image_id; out_dists[(size_t)q * k + i] = it->dist; }
+          out_counts[q] = i;
+        }
+      }
+    });
+  }
+  for (auto& t : th) t.join();
+  vc_shim_mpi_set_world(1);
+  vc_shim_mpi_set_rank(0);
+  return 0;
+}
+
 // linear_search.cc:39-64 over a caller-owned code array, nq queries fanned out
 // over n_procs forked children (the reference function is single-threaded and
 // keeps its state in globals, so processes - not threads - are the only way to

@@ -29,6 +29,7 @@ def lib():
         L.ref_mih_search.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p, u32p, u32p, u32p, u64p]
         L.ref_mem_mih_search.argtypes = L.ref_mih_search.argtypes
         L.ref_linear_search.argtypes = [u8p, C.c_int, C.c_int, C.c_uint32, u32p, u32p, u32p]
+        L.ref_mem_fixed_radius_search.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p, u32p, u32p, u64p]
         L.ref_mem_build.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_uint32]
         L.ref_mem_linear_search.argtypes = [u8p, C.c_uint64, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u32p, u32p, u32p]
         L.ref_kv_entries.restype = C.c_uint64
@@ -135,6 +136,21 @@ class RefMem:
 
     def mih_search(self, queries, k, approximate=False):
         return _mih(lib().ref_mem_mih_search, queries, self.nbytes, self.m, k, approximate, self.n)
+
+    def fixed_radius_search(self, queries, k, max_radius):
+        """Radii 0 .. max_radius, no stop rule (config C5): the reference's own probing and verification under a subclass that
+        leaves out the stop test (FixedRadiusWorker, ref_driver.cc).  Returns ids, dists (descending), counts, sub_reads."""
+        queries = np.ascontiguousarray(queries, dtype=np.uint8)
+        nq = queries.shape[0]
+        ids = np.full((nq, k), 0xFFFFFFFF, dtype=np.uint32)
+        dists = np.full((nq, k), 0xFFFFFFFF, dtype=np.uint32)
+        counts = np.zeros(nq, dtype=np.uint32)
+        sub_reads = np.zeros((nq, self.m), dtype=np.uint64)
+        rc = lib().ref_mem_fixed_radius_search(_u8(queries), nq, self.nbytes, self.m, k, int(max_radius), int(self.n), _u32(ids), _u32(dists),
+                                               _u32(counts), sub_reads.ctypes.data_as(C.POINTER(C.c_uint64)))
+        if rc != 0:
+            raise RuntimeError("reference fixed-radius search failed")
+        return ids, dists, counts, sub_reads
 
     def linear_search(self, queries, k, n_procs=1):
         queries = np.ascontiguousarray(queries, dtype=np.uint8)

@@ -66,6 +66,24 @@ def test_restatement_reproduces_reference_search_at_256_bits(n, bits, m, k, nq, 
         assert (rrad == bits // m).all()
 
 
+@pytest.mark.parametrize("n,bits,m,k,nq,max_radius", [
+    (3000, 256, 16, 1000, 2, 0), (3000, 256, 16, 1000, 2, 1), (3000, 256, 16, 1000, 2, 2), (3000, 256, 16, 1000, 2, 3),   # config C5's sweep
+    (20000, 64, 4, 10, 4, 2), (2000, 128, 8, 100, 3, 1), (500, 64, 8, 10, 3, 8),
+])
+def test_restatement_reproduces_reference_fixed_radius_search(n, bits, m, k, nq, max_radius):
+    """Fixed-radius mode (config C5: radii 0 .. r, no stop rule, the k best of what was found, fewer than k when fewer were
+    found).  Reference side: its own search_R_neighbors / enumerate_entry / gather_vectors under a subclass that leaves out the
+    stop test (FixedRadiusWorker, oracle/ref_driver.cc)."""
+    codes, queries = _data(n, bits, nq)
+    rid, rd, rc, rsub = F.RefMem(codes, m).fixed_radius_search(queries, k, max_radius)
+    oid, od, oc, ost = R.Index(codes, m).search(queries, k, order=R.ORDER_REFERENCE, stop=R.STOP_REF4, max_radius=max_radius)
+    np.testing.assert_array_equal(oc, rc)
+    np.testing.assert_array_equal(od, rd)
+    np.testing.assert_array_equal(oid, rid)
+    for q in range(nq):
+        assert ost[q]["probes"] == rsub[q].sum()
+
+
 def test_restatement_reproduces_reference_linear_scan_exactly():
     codes, queries = _data(30000, 64, 6)
     store = F.RefStore(codes, 0)
