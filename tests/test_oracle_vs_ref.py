@@ -84,8 +84,9 @@ def test_restatement_reproduces_reference_fixed_radius_search(n, bits, m, k, nq,
         assert ost[q]["probes"] == rsub[q].sum()
 
 
-def test_restatement_reproduces_reference_linear_scan_exactly():
-    codes, queries = _data(30000, 64, 6)
+@pytest.mark.parametrize("n,bits", [(30000, 64), (8000, 128), (8000, 256)])
+def test_restatement_reproduces_reference_linear_scan_exactly(n, bits):
+    codes, queries = _data(n, bits, 6)
     store = F.RefStore(codes, 0)
     store.put_main_table()
     rid, rd, rc = store.linear_search(queries, 100)
