@@ -472,6 +472,25 @@ int ref_mem_mih_search(const uint8_t* queries, int nq, int nbytes, int n_tables,
   return 0;
 }
 
+// The reference's ImageBitmap (src/bitmap.cc:22-38, unmodified) over a caller-owned word array: op 0 = get_idx, 1 = set_idx,
+// 2 = reset_idx for every bit index of the list, in order; get results go to out (0 / 1).  The class frees what it is
+// given (bitmap.cc:16-21), so it works on a malloc'ed copy that is copied back.
+int ref_bitmap_ops(uint32_t* words, uint64_t n_bytes, const uint64_t* bits, const int* ops, uint64_t n_ops, uint8_t* out) {
+  void* copy = malloc(n_bytes);
+  if (!copy) return 1;
+  memcpy(copy, words, n_bytes);
+  {
+    ImageBitmap bmp(n_bytes, copy);
+    for (uint64_t i = 0; i < n_ops; ++i) {
+      if (ops[i] == 0) out[i] = bmp.get_idx(bits[i]) ? 1 : 0;
+      else if (ops[i] == 1) bmp.set_idx(bits[i]);
+      else bmp.reset_idx(bits[i]);
+    }
+    memcpy(words, bmp.data(), n_bytes);
+  }                                                      // ~ImageBitmap frees the copy
+  return 0;
+}
+
 // Fixed-radius search (BASELINE config C5: radii 0 .. max_radius, no stop rule, the k best of what was found).  The reference
 // has no such entry point, but its pieces are reachable from a subclass (the members are protected, search_worker.h:35-63):
 // candidate generation is the reference's own search_R_neighbors / enumerate_entry (probe order, bucket reads, distances)

@@ -29,6 +29,7 @@ def lib():
         L.ref_mih_search.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p, u32p, u32p, u32p, u64p]
         L.ref_mem_mih_search.argtypes = L.ref_mih_search.argtypes
         L.ref_linear_search.argtypes = [u8p, C.c_int, C.c_int, C.c_uint32, u32p, u32p, u32p]
+        L.ref_bitmap_ops.argtypes = [u32p, C.c_uint64, u64p, C.POINTER(C.c_int), C.c_uint64, u8p]
         L.ref_mem_fixed_radius_search.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p, u32p, u32p, u64p]
         L.ref_mem_build.argtypes = [u8p, C.c_uint64, C.c_int, C.c_int, C.c_uint32]
         L.ref_mem_linear_search.argtypes = [u8p, C.c_uint64, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u32p, u32p, u32p]
@@ -163,3 +164,17 @@ class RefMem:
         if rc != 0:
             raise RuntimeError("reference linear search failed")
         return ids, dists, counts
+
+
+def bitmap_ops(words, bits, ops):
+    """Runs get (0) / set (1) / reset (2) on the reference's own ImageBitmap (src/bitmap.cc) over `words` (uint32 array, modified
+    in place); returns the get results (0 / 1; undefined where the op was not a get)."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint64)
+    ops = np.ascontiguousarray(ops, dtype=np.int32)
+    out = np.zeros(bits.size, dtype=np.uint8)
+    rc = lib().ref_bitmap_ops(_u32(words), words.nbytes, bits.ctypes.data_as(C.POINTER(C.c_uint64)), ops.ctypes.data_as(C.POINTER(C.c_int)),
+                              bits.size, _u8(out))
+    if rc != 0:
+        raise RuntimeError("reference bitmap ops failed")
+    return out
+

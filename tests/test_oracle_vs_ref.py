@@ -155,3 +155,39 @@ def test_contract_p3_p4_canonical_vs_reference(n, bits, m, k):
         assert cst[q]["radius"] in (rrad[q], rrad[q] + 1)
         if cst[q]["radius"] != rrad[q]:
             assert dk == 4 * (rrad[q] + 1)
+
+
+def test_bitmap_restatement_matches_reference_bitmap():
+    """a10: ImageBitmap::get_idx / set_idx / reset_idx (src/bitmap.cc:22-38, unmodified, through ref_bitmap_ops) against the
+    restatement's vo_bitmap_* on a random op sequence - including bit 31 of a word, where the reference shifts a signed 1 -
+    and a11: the occupancy bitmap of a table is the reference class fed with every code's key."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    n_bits = 1 << 16
+    bits = rng.integers(0, n_bits, 6000).astype(np.uint64)
+    bits[:64] = np.arange(64, dtype=np.uint64) * 32 + 31          # the sign bit of every one of the first words
+    ops = rng.choice([0, 1, 1, 2], size=bits.size).astype(np.int32)
+    ref_words = np.zeros(n_bits // 32, dtype=np.uint32)
+    ref_get = F.bitmap_ops(ref_words, bits, ops)
+    L = R.lib()
+    words = np.zeros(n_bits // 32, dtype=np.uint32)
+    wp = words.ctypes.data_as(C.POINTER(C.c_uint32))
+    for i, (b, op) in enumerate(zip(bits.tolist(), ops.tolist())):
+        if op == 0:
+            assert L.vo_bitmap_get(wp, b) == ref_get[i]
+        elif op == 1:
+            L.vo_bitmap_set(wp, b)
+        else:
+            L.vo_bitmap_reset(wp, b)
+    np.testing.assert_array_equal(words, ref_words)
+    # occupancy of a table (generate_bitmap.cc:99-125 sets one bit per code and table): s = 16 and s = 8
+    for bits_, m in [(64, 4), (64, 8)]:
+        codes, _ = _data(4000, bits_, 1)
+        ix = R.Index(codes, m)
+        sub = bits_ // m // 8
+        for t in (0, m - 1):
+            keys = np.array([R.binary_to_int(codes[i, t * sub:(t + 1) * sub]) for i in range(codes.shape[0])], dtype=np.uint64)
+            ref_occ = np.zeros((1 << (8 * sub)) // 32, dtype=np.uint32)
+            F.bitmap_ops(ref_occ, keys, np.ones(keys.size, dtype=np.int32))
+            np.testing.assert_array_equal(ix.occupancy_bitmap(t), ref_occ)
+
