@@ -46,6 +46,8 @@ def lib():
         L.vo_merge_topk.restype = C.c_uint32
         L.vo_merge_topk.argtypes = [u64p, C.c_uint32, C.c_uint32, u64p]
         L.vo_synth_codes.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, u8p]
+        L.vo_scan_synth.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, u8p, C.c_uint32, C.c_uint32,
+                                    C.c_int, C.c_int, u64p]
         L.vo_synth_word.restype = C.c_uint64
         L.vo_synth_word.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         L.vo_bitmap_get.restype = C.c_int
@@ -150,3 +152,34 @@ def merge_topk(lists, k):
     n = lib().vo_merge_topk(lists.ctypes.data_as(C.POINTER(C.c_uint64)), lists.shape[0], k,
                             out.ctypes.data_as(C.POINTER(C.c_uint64)))
     return out[:n]
+
+
+def _scan_synth_range(args):
+    seed, first_id, stride, i0, i1, nbytes, queries, k, m, max_radius = args
+    out = np.empty((queries.shape[0], k), dtype=np.uint64)
+    lib().vo_scan_synth(seed, first_id, stride, i0, i1, nbytes, _u8(queries), queries.shape[0], k, m, max_radius,
+                        out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return out
+
+
+def scan_synth(seed, first_id, stride, n, nbytes, queries, k, m=0, max_radius=-1, n_procs=1):
+    """Canonical top-k of every query over the n synthetic codes with ids first_id + i * stride, generated on the fly
+    (vo_scan_synth): [nq, k] uint64 packed words, ascending, UINT64_MAX padded.  m > 0 and max_radius >= 0: among the
+    candidates of the fixed-radius MIH search only.  n_procs > 1 forks workers over ranges of i and merges their lists."""
+    queries = np.ascontiguousarray(queries, dtype=np.uint8).reshape(-1, nbytes)
+    n_procs = max(1, min(int(n_procs), int(n) // 1_000_000 or 1))
+    bounds = [n * p // n_procs for p in range(n_procs + 1)]
+    jobs = [(seed, first_id, stride, bounds[p], bounds[p + 1], nbytes, queries, k, m, max_radius) for p in range(n_procs)]
+    if n_procs == 1:
+        parts = [_scan_synth_range(jobs[0])]
+    else:
+        import multiprocessing as mp
+        lib()                                            # built before the fork
+        with mp.get_context("fork").Pool(n_procs) as pool:
+            parts = pool.map(_scan_synth_range, jobs)
+    out = np.empty((queries.shape[0], k), dtype=np.uint64)
+    for q in range(queries.shape[0]):
+        merged = merge_topk(np.stack([p[q] for p in parts]), k)
+        out[q, : len(merged)] = merged
+        out[q, len(merged):] = np.iinfo(np.uint64).max
+    return out

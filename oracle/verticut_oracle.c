@@ -419,3 +419,39 @@ void vo_synth_codes(uint64_t seed, uint64_t first_id, uint64_t n, int nbytes, ui
       memcpy(out + i * nbytes + (size_t)w * 8, &v, 8);
     }
 }
+
+/* Streaming form of a8 (linear_search.cc:39-64) over the SYNTHETIC database, for checks at sizes whose codes no host can
+ * hold: codes i0 <= i < i1 of a shard whose code i has id first_id + i * stride are generated on the fly and offered to one
+ * canonical top-k per query.  With m > 0 and max_radius >= 0 only those codes count that the fixed-radius MIH search reaches:
+ * some table t holds them in a bucket within substring distance max_radius of the query's substring t - exactly the union of
+ * the buckets SearchWorker::search_R_neighbors / enumerate_entry visit for radii 0 .. max_radius (search_worker.cc:222-264;
+ * pinned against vo_mih_search in tests/test_oracle_vs_ref.py).  out_keys: [nq][k] packed words, UINT64_MAX padded. */
+void vo_scan_synth(uint64_t seed, uint64_t first_id, uint64_t stride, uint64_t i0, uint64_t i1, int nbytes, const uint8_t* queries,
+                   uint32_t nq, uint32_t k, int m, int max_radius, uint64_t* out_keys) {
+  const int words = nbytes / 8, sub = m > 0 ? nbytes / m : 0;
+  uint64_t base[8];
+  uint8_t code[64];
+  vo_topk* tk = (vo_topk*)malloc(sizeof(vo_topk) * (nq ? nq : 1));
+  for (uint32_t q = 0; q < nq; ++q) { tk[q].a = out_keys + (size_t)q * k; tk[q].n = 0; tk[q].k = k; }
+  for (int w = 0; w < words; ++w) base[w] = splitmix64(seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(w + 1)));   /* vo_synth_word, hoisted */
+  for (uint64_t i = i0; i < i1; ++i) {
+    const uint64_t id = first_id + i * stride;
+    for (int w = 0; w < words; ++w) { const uint64_t v = splitmix64(base[w] + id); memcpy(code + 8 * w, &v, 8); }
+    for (uint32_t q = 0; q < nq; ++q) {
+      const uint8_t* qc = queries + (size_t)q * nbytes;
+      if (m > 0 && max_radius >= 0) {
+        int reached = 0;
+        for (int t = 0; t < m && !reached; ++t) {   /* substrings are 1, 2 or 4 bytes: compute_hamming_dist counts whole 32-bit words only */
+          int sd = 0;
+          for (int b = 0; b < sub; ++b) sd += __builtin_popcount((unsigned)(code[t * sub + b] ^ qc[t * sub + b]));
+          reached = sd <= max_radius;
+        }
+        if (!reached) continue;
+      }
+      topk_offer(&tk[q], pack((uint32_t)vo_hamming(code, qc, nbytes), (uint32_t)id));
+    }
+  }
+  for (uint32_t q = 0; q < nq; ++q)
+    for (size_t j = tk[q].n; j < k; ++j) out_keys[(size_t)q * k + j] = UINT64_MAX;
+  free(tk);
+}

@@ -84,3 +84,85 @@ def test_batched_state_is_clean_between_calls(oracle):
         np.testing.assert_array_equal(ids[:5], oid)
         np.testing.assert_array_equal(dists[:5], od)
     ix.close()
+
+
+def test_batched_large_k_stays_on_the_batched_path(oracle):
+    """k = 1000 (config C5): the candidate buffers scale with k, so no query overflows into the per-query kernel."""
+    n, nq, k = 400_000, 24, 1000
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    ix = capi.Index(64, 4)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    q = oracle.synth_codes(67890, 0, nq, 8)
+    ids, dists, counts, _ = ix.search_mih(q, k)
+    assert ix.get_param("mih.last_batched") == 1 and ix.get_param("mih.last_redo") == 0
+    oid, od, oc = oracle.linear_search(codes, q, k)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    ix.close()
+
+
+@pytest.mark.parametrize("bits,m,r,k", [(256, 16, 2, 1000), (128, 8, 2, 300)])
+def test_batched_fixed_radius_large_k(oracle, bits, m, r, k):
+    """Config C5's shape in small: fixed radius, k = 1000, 256-bit codes - top-k among the candidates found, vs the oracle."""
+    n, nq = 60_000, 6
+    codes = oracle.synth_codes(12345, 0, n, bits // 8)
+    ix = capi.Index(bits, m)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    queries = codes[:nq].copy()
+    queries[:, 0] ^= 1
+    ids, dists, counts, stats = ix.search_mih(queries, k, max_radius=r)
+    assert ix.get_param("mih.last_batched") == 1 and ix.get_param("mih.last_redo") == 0
+    oid, od, oc, _ = oracle.Index(codes, m).search(queries, k, max_radius=r)
+    np.testing.assert_array_equal(counts, oc)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    ix.close()
+
+
+@pytest.mark.parametrize("cap", [64, 150, 700])
+def test_batched_overflow_redoes_only_the_overflowed_queries(oracle, cap):
+    """A candidate buffer that overflows (forced here with a tiny mih.cap) takes that query - not the whole batch - through
+    the per-query kernel; the answers stay exact either way."""
+    n, nq, k = 300_000, 40, 50
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    ix = capi.Index(64, 4)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    ix.set_param("mih.cap", cap)
+    ix.set_param("mih.boot_sample", 64)                      # loose first thresholds: plenty of appends
+    q = oracle.synth_codes(67890, 0, nq, 8)
+    q[:8] = codes[:8]                                        # and a few queries that sit on database codes
+    ids, dists, counts, st = ix.search_mih(q, k)
+    redo = ix.get_param("mih.last_redo")
+    assert ix.get_param("mih.last_batched") == 1
+    if cap <= 150:
+        assert 0 < redo <= nq
+    oid, od, oc = oracle.linear_search(codes, q, k)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    np.testing.assert_array_equal(counts, oc)
+    assert (st["n_results"] == k).all()
+    ix.close()
+
+
+def test_batched_settle_folds_more_candidates_than_fit_in_shared_memory(oracle):
+    """k = 2000 with a 16 K-entry buffer: the settle kernel sorts 4096 entries at a time and must fold the rest exactly."""
+    n, nq, k = 200_000, 5, 2000
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    ix = capi.Index(64, 4)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    ix.set_param("mih.boot_sample", 64)
+    q = oracle.synth_codes(67890, 0, nq, 8)
+    ids, dists, counts, _ = ix.search_mih(q, k)
+    assert ix.get_param("mih.last_batched") == 1
+    oid, od, oc = oracle.linear_search(codes, q, k)
+    np.testing.assert_array_equal(ids, oid)
+    np.testing.assert_array_equal(dists, od)
+    ix.close()

@@ -116,6 +116,18 @@ def test_garbage_closes_the_connection_only(server):
     assert Conn(server).call(1, "ping", ["next client"]) == [1, 1, None, "next client"]
 
 
+def test_item_flood_and_oversized_requests_close_the_connection_only(server):
+    """A request is seven items and tens of bytes: a message that declares thousands of items (each decoded Value costs ~100
+    bytes of server memory) or keeps streaming without completing an object is dropped, the server lives on."""
+    c = Conn(server)
+    c.s.sendall(b"\xdc\x10\x00" + b"\xc0" * 4096)          # array16 of 4096 nils
+    assert c.s.recv(16) == b""
+    c = Conn(server)
+    c.s.sendall(b"\x94\x00\x01\xa4ping\x91\xdb\x00\x40\x00\x00" + b"a" * ((1 << 20) + 4096))     # a ping whose str32 announces 4 MB
+    assert c.s.recv(16) == b""
+    assert Conn(server).call(1, "ping", ["next client"]) == [1, 1, None, "next client"]
+
+
 def test_client_cli_against_the_stub(server, stub):
     cli = os.path.join(HOST, "bin", "image-search-client")
     r = subprocess.run([cli, "127.0.0.1", str(server), "ping", "hello"], capture_output=True, text=True, timeout=30)

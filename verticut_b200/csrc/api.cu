@@ -123,7 +123,8 @@ struct vc_index {
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
   uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
-  int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(4096, 16 k))
+  int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(16384, 16 k))
+  int64_t mih_cap = 0;            // candidate-buffer entries per query (0: bmih_cap_for(k)); small values force the overflow path in tests
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
   // tensor-core verify kernel (tcverify.cuh): 0 never (default: measured slower than the POPC kernels),
   // 1 whenever legal, -1 by size (scan: >= scan.tc_min queries; MIH: steps with >= mih.tc_ratio queries per code)
@@ -135,7 +136,7 @@ struct vc_index {
   vc_allreduce_fn allreduce_fn = nullptr;
   void* allreduce_user = nullptr;
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
-  int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0;
+  int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0, last_mih_redo = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
   int64_t profile = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -228,7 +229,7 @@ void vc_index_destroy(vc_index* ix) {
   if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
   for (cudaEvent_t e : ix->lev) if (e) cudaEventDestroy(e);
   DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate,
-                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_redo};
+                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_redo, &ix->b_idh, &ix->b_trace};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
   for (PinBuf* b : pb) b->release();
@@ -687,7 +688,8 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   int rc;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
+  const uint32_t cap = bmih_cap_for(k);
+  const size_t o_gbuf = take((size_t)nq * cap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
                o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
                o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
                o_xhist = take((size_t)nq * Cfg::HB * 4), o_ctr = take(128), o_tab = take(sizeof(TableDev));
@@ -696,7 +698,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   uint32_t* ctr = (uint32_t*)(sb + o_ctr);
   BmihParams p;
   memset(&p, 0, sizeof p);
-  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = 1; p.sbits = 0; p.max_radius = 0;
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = 1; p.sbits = 0; p.max_radius = 0; p.cap = cap;
   p.scan_mode = 1; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
   TableDev pseudo;
   memset(&pseudo, 0, sizeof pseudo);
@@ -808,7 +810,7 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   // (candidates appended per query ~ 15-20 k before the thresholds settle: automatic only while that fits the buffer)
   const bool batched = ix->scan_batched > 0 || (ix->scan_batched < 0 && nq >= (uint32_t)ix->scan_batched_min && k <= 128);
   ix->last_scan_batched = 0;
-  if (batched && k < (uint32_t)kBmihCap / 2 && ix->n > 0 && ix->n < 0xFFFFFFFFull) {
+  if (batched && k < (uint32_t)kBmihSort / 2 && ix->n > 0 && ix->n < 0xFFFFFFFFull) {
     if (ix->W == 1) return scan_batched<1>(ix, d_queries, nq, k, d_out_keys, st);
     if (ix->W == 2) return scan_batched<2>(ix, d_queries, nq, k, d_out_keys, st);
     return scan_batched<4>(ix, d_queries, nq, k, d_out_keys, st);
@@ -924,8 +926,9 @@ static int launch_mih(vc_index* ix, const MihParams& p, cudaStream_t st) {
 }
 
 static int mih_per_query(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
-                         uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
+                         uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st, const uint32_t* d_qsel = nullptr) {
   MihParams p;
+  p.qsel = d_qsel;
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = ix->m; p.sbits = ix->sbits;
   p.BUFM = pow2_at_least(k + kMihWbuf);
   p.approximate = approximate; p.max_radius = max_radius;
@@ -966,7 +969,8 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   // ---- workspace ---------------------------------------------------------------------------------------
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_gbuf = take((size_t)nq * kBmihCap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
+  const uint32_t cap = ix->mih_cap > 0 ? (uint32_t)ix->mih_cap : bmih_cap_for(k);
+  const size_t o_gbuf = take((size_t)nq * cap * 8), o_taukey = take((size_t)nq * 8), o_hist = take((size_t)nq * Cfg::HB * 4),
                o_cnt = take((size_t)nq * 4), o_tau = take((size_t)nq * 4), o_flag = take((size_t)nq * 4), o_rad = take((size_t)nq * 4),
                o_probes = take((size_t)nq * 8), o_cands = take((size_t)nq * 8), o_actA = take((size_t)nq * 4), o_actB = take((size_t)nq * 4),
                o_xhist = take((size_t)nq * Cfg::HB * 4), o_globkey = take((size_t)nq * 8),
@@ -977,7 +981,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   uint32_t* ctr = (uint32_t*)(sb + o_ctr);            // [0] n_items  [1] item_cursor  [2] n_next  [3] any_overflow
   BmihParams p;
   memset(&p, 0, sizeof p);
-  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = m; p.sbits = sbits; p.radius = 0; p.max_radius = max_radius;
+  p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = m; p.sbits = sbits; p.radius = 0; p.max_radius = max_radius; p.cap = cap;
   p.tables = ix->d_tab; p.active = nullptr; p.n_active = 0;
   {
     // work-item length: about one average bucket, between 2 and 8 CTA steps
@@ -1000,7 +1004,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   const uint32_t popc_cpi = p.cpi;
   const bool tc_possible = ix->mih_tc != 0;
   p.qt = kBmihQT; p.cpi_alt = kTcCpi; p.qt_alt = 128; p.n_items_alt = tc_possible ? ctr + 5 : nullptr;
-  ix->last_mih_tc_steps = 0;
+  ix->last_mih_tc_steps = 0; ix->last_mih_redo = 0;
   unsigned long long prev_codes = 0, prev_pairs = 0, prev_exec = 0;
   ix->step_codes.clear(); ix->step_pairs.clear(); ix->step_exec.clear();
   p.gbuf = (uint64_t*)(sb + o_gbuf); p.gcnt = (uint32_t*)(sb + o_cnt); p.gtaukey = (uint64_t*)(sb + o_taukey);
@@ -1184,13 +1188,17 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, d_stats);
   ix->launches++;
   if (h_ctr[3]) {
-    // some candidate buffer overflowed (heavy ties): those queries take the per-query kernel's exact answer
-    if ((rc = ix->b_redo.ensure((size_t)nq * k * 8 + (size_t)nq * sizeof(vc_query_stats)))) return rc;
-    uint64_t* rk = (uint64_t*)ix->b_redo.p;
-    vc_query_stats* rs = (vc_query_stats*)(rk + (size_t)nq * k);
-    if ((rc = mih_per_query(ix, d_queries, nq, k, 0, max_radius, rk, rs, st))) return rc;
-    bmih_patch_kernel<<<nq, 128, 0, st>>>(p.gflag, k, rk, rs, d_out_keys, d_stats);
+    // some candidate buffers overflowed (heavy ties): those queries - and only those - take the per-query kernel's exact answer
+    if ((rc = ix->b_redo.ensure((size_t)nq * 4 + 256))) return rc;
+    uint32_t* rl = (uint32_t*)ix->b_redo.p;
+    CU(cudaMemsetAsync(ctr + 2, 0, 4, st));
+    bmih_redo_list_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p.gflag, nq, rl, ctr + 2);
+    uint32_t n_redo = 0;
+    CU(cudaMemcpyAsync(&n_redo, ctr + 2, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     ix->launches++;
+    ix->last_mih_redo = n_redo;
+    if (n_redo && (rc = mih_per_query(ix, d_queries, n_redo, k, 0, max_radius, d_out_keys, d_stats, st, rl))) return rc;
   }
   CU(cudaGetLastError());
   unsigned long long h_bc = 0, tcs[3] = {0, 0, 0};
@@ -1215,8 +1223,10 @@ int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t
   cudaStream_t st = (cudaStream_t)stream;
   // Bucket-stationary batching pays when several queries share a bucket and buckets are long enough to
   // fill a CTA step; it needs dense tables and no distinct-candidate count (approximate mode).
-  const bool legal = ix->sbits <= 16 && !(approximate != 0 && max_radius < 0) && k < (uint32_t)kBmihCap / 2;
-  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && (ix->n >> ix->sbits) >= (uint64_t)ix->mih_min_bucket);
+  const bool legal = ix->sbits <= 16 && !(approximate != 0 && max_radius < 0) && k < (uint32_t)kBmihSort / 2;
+  // id-sharded (an all-reduce hook is set): only the batched path calls the hook, so the choice must not depend on this
+  // shard's size - shard sizes differ by one code when N % G != 0, and one rank issuing collectives the others do not is a hang
+  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && (ix->allreduce_fn != nullptr || (ix->n >> ix->sbits) >= (uint64_t)ix->mih_min_bucket));
   ix->last_mih_batched = 0;
   if (legal && want) {
     if (ix->W == 1) return mih_batched<1>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
@@ -1318,9 +1328,16 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.tc_ratio")) ix->mih_tc_ratio = value;
   else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
+  else if (!strcmp(name, "mih.cap")) {
+    if (value < 0 || value > (1 << 20)) return fail(VC_ERR_ARG, "mih.cap must be in [0, 2^20]");
+    ix->mih_cap = value;
+  }
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
-  else if (!strcmp(name, "mih.cpi_steps")) ix->mih_cpi_steps = value;
+  else if (!strcmp(name, "mih.cpi_steps")) {
+    if (value < 0 || value > 1024) return fail(VC_ERR_ARG, "mih.cpi_steps must be in [0, 1024]");     // the hit queue packs (position in the item) << 5
+    ix->mih_cpi_steps = value;
+  }
   else if (!strcmp(name, "mih.wide")) ix->mih_wide = value;
   else if (!strcmp(name, "mih.min_bucket")) ix->mih_min_bucket = value;
   else if (!strcmp(name, "mih.table_steps")) ix->mih_table_steps = value;
@@ -1362,6 +1379,7 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "mih.batched")) *value = ix->mih_batched;
   else if (!strcmp(name, "mih.last_batched")) *value = ix->last_mih_batched;
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;
+  else if (!strcmp(name, "mih.last_redo")) *value = ix->last_mih_redo;
   else if (!strcmp(name, "mih.last_items")) *value = ix->last_mih_items;
   else if (!strcmp(name, "mih.last_bucket_codes")) *value = ix->last_mih_bucket_codes;
   else if (!strncmp(name, "mih.step_exec.", 14)) {

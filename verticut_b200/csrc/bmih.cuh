@@ -34,7 +34,9 @@ namespace vc {
 #endif
 constexpr int kBmihThreads = VC_BMIH_THREADS;
 constexpr int kBmihQT = 32;          // queries per work item
-constexpr int kBmihCap = 4096;       // candidate-buffer entries per query
+constexpr int kBmihSort = 4096;      // entries the settle kernel sorts at a time (shared memory); k must stay below half of it
+constexpr int kBmihCapMin = 4096;    // candidate-buffer entries per query: at least this, see bmih_cap_for
+constexpr int kBmihHitQ = 128;       // deferred hits per warp of the verify kernel (bv_hitq)
 constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (short-bucket variant)
 #ifndef VC_VERIFY_CTAS
 #define VC_VERIFY_CTAS 4   // 64-bit codes: 4 CTAs (32 warps, 64 registers) per SM - the kernel is latency-bound, 15.5 instead of 16.7 ms per search
@@ -43,7 +45,10 @@ constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (s
 #define VC_VERIFY_CTAS_W2 3   // 128- and 256-bit codes: not re-measured at 4 CTAs per SM yet
 #endif
 #ifndef VC_KEY_SUBST
-#define VC_KEY_SUBST 0       // experimental (not measured yet): bucket key substituted into the staged queries, see bmih_verify_kernel
+#define VC_KEY_SUBST 1       // bucket key substituted into the staged queries (a sharper one-POPC-per-64-bit filter), see bmih_verify_kernel
+#endif
+#ifndef VC_HIT_QUEUE
+#define VC_HIT_QUEUE 1       // codes that pass the filter are queued per warp and re-checked 32 at a time instead of inside the distance loop
 #endif
 #ifndef VC_PF_DIST
 #define VC_PF_DIST 4
@@ -76,6 +81,7 @@ struct BmihParams {
   uint32_t r_lo;                // lowest radius of the step: radii [r_lo, radius] are probed together (normally r_lo == radius)
   uint32_t t_begin, t_end;      // ... and its tables [t_begin, t_end): a whole radius (0, m) or one table of it
   uint32_t cpi;                 // codes per work item (multiple of the step size)
+  uint32_t cap;                 // candidate-buffer entries per query (bmih_cap_for(k))
   uint32_t boot_sample;         // codes per query the threshold bootstrap looks at (0: the default)
   uint32_t count_in_write;      // items kernel: the writing pass is the only pass, it also keeps the statistics
   uint32_t qt;                  // queries per work item (kBmihQT for the POPC kernel, up to 256 for the tensor-core kernel)
@@ -98,7 +104,7 @@ struct BmihParams {
   unsigned long long* exec_pairs;     // [1] code-query tests the verify kernel really executed (less: queries leave buckets at their k-th id)
   uint32_t* item_cursor;        // [1]
   // per-query state
-  uint64_t* gbuf;               // [nq][kBmihCap]
+  uint64_t* gbuf;               // [nq][cap]
   uint32_t* gcnt;               // [nq]
   uint64_t* gtaukey;            // [nq]
   uint64_t* gglobkey;           // [nq] id-sharded search: a key that at least k codes of the WHOLE database are below (or kEmptyKey)
@@ -233,6 +239,15 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
 }
 
 // ---- 3. verification ---------------------------------------------------------------------------------------
+// candidate-buffer entries per query for a search with this k.  A step that looks at C candidates after S were known appends
+// about k ln(C / S) of them before the thresholds have settled (each new code is among the k best so far with probability
+// k / seen), so the buffer scales with k: 4096 entries for k <= 512, 8 k rounded up to a power of two above that.
+__host__ __device__ inline uint32_t bmih_cap_for(uint32_t k) {
+  uint32_t cap = kBmihCapMin;
+  while (cap < 8u * k) cap <<= 1;
+  return cap;
+}
+
 // rare path: a code whose exact distance d passed the staged threshold tau_s of query qid.
 // ghist[q][b] holds CUMULATIVE counts: distinct known codes at distance <= b (maintained for b below the
 // threshold only - bins at or above it are never consulted again, since thresholds only fall).
@@ -262,23 +277,12 @@ __device__ __forceinline__ void bmih_append_impl(const BmihParams* pp, uint32_t 
   constexpr int HB = BmihCfg<W>::HB;
   uint32_t* gc = p.ghist + (size_t)qid * HB;
   const uint32_t lim = min(tau_s, (uint32_t)(64 * W + 1));      // bins d .. lim-1 count this code
-#if VC_APPEND_OVERLAP
-  // the two atomics whose results are needed travel together (one L2 round trip instead of two)
   const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
-  uint32_t old = 0;
-  if (d < lim) old = atomicAdd(&gc[lim - 1], 1u);
-  if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
-  else atomicOr(&p.gflag[qid], 1u);
-  if (d >= lim) return;
-  for (uint32_t b0 = d; b0 + 1 < lim; ++b0) atomicAdd(&gc[b0], 1u);              // fire and forget
-#else
-  const uint32_t slot = atomicAdd(&p.gcnt[qid], 1u);
-  if (slot < (uint32_t)kBmihCap) p.gbuf[(size_t)qid * kBmihCap + slot] = key;
+  if (slot < p.cap) p.gbuf[(size_t)qid * p.cap + slot] = key;
   else atomicOr(&p.gflag[qid], 1u);
   if (d >= lim) return;
   for (uint32_t b0 = d; b0 + 1 < lim; ++b0) atomicAdd(&gc[b0], 1u);              // fire and forget
   const uint32_t old = atomicAdd(&gc[lim - 1], 1u);
-#endif
   if (old + 1 >= p.k) {                                        // k codes are now strictly inside the threshold
     uint32_t nt = lim - 1;
     while (nt > 0 && __ldcg(&gc[nt - 1]) >= p.k) --nt;
@@ -298,34 +302,63 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
 constexpr int kBmihQSMax = 12;                                      // BmihCfg<4>::QS
 __shared__ __align__(16) uint32_t bv_qrec[(kBmihThreads / 32) * kBmihQT * kBmihQSMax];
 __shared__ uint32_t bv_qid[kBmihThreads / 32][kBmihQT];
+__shared__ uint32_t bv_hitq[kBmihThreads / 32][kBmihHitQ];          // deferred hits: (code position - item start) << 5 | staged query slot
+__shared__ unsigned long long bv_pairs[kBmihThreads / 32];          // tests executed by the warp (statistics)
+__shared__ const uint64_t* bv_codes[kMaxTables];                    // table payload pointers, fetched once per CTA
+__shared__ const uint32_t* bv_ids[kMaxTables];
+
+// One code (position j of table t, bucket order) that passed the filter for staged query qq of this warp: the exact distance
+// against the staged record, and - for the few that really beat the threshold - de-duplication and append.  The code is read
+// again from global memory (it was streamed through this SM a moment ago: an L2 hit).
 template <int W, int QS>
-__device__ __noinline__ void bmih_append_staged(const BmihParams* pp, uint32_t qq, uint32_t t, uint32_t d, uint32_t j, CodeRegs<W> c,
-                                                uint32_t tau_s) {
+__device__ __forceinline__ void bmih_process_hit(const BmihParams* pp, uint32_t t, uint32_t j, uint32_t qq) {
   const uint32_t warp = threadIdx.x >> 5;
-#if VC_KEY_SUBST
-  // d and tau_s are relative to the staged record: the substring of table t is not part of them (bmih_verify_kernel)
   uint32_t* rec = bv_qrec + warp * (kBmihQT * QS) + qq * QS;
+  CodeRegs<W> c;
+  const uint2* src = reinterpret_cast<const uint2*>(bv_codes[t] + (size_t)j * W);
+#pragma unroll
+  for (int i = 0; i < W; ++i) { const uint2 v = __ldg(src + i); c.w[2 * i] = v.x; c.w[2 * i + 1] = v.y; }
+  const uint32_t tau = *(volatile uint32_t*)&rec[2 * W];
+  const uint32_t d = hamming_exact<W>(c.w, rec);
+  if (d > tau) return;
   const uint32_t qid = bv_qid[warp][qq];
+#if VC_KEY_SUBST
+  // d and tau are relative to the staged record: the substring of table t is not part of them (bmih_verify_kernel)
   const uint32_t r_sub = pp->scan_mode ? 0u : rec[2 * W + 1];
-  bmih_append_impl<W>(pp, qid, t, d + r_sub, j, c, rec, tau_s + r_sub, pp->queries + (size_t)qid * 2 * W, r_sub);
+  bmih_append_impl<W>(pp, qid, t, d + r_sub, j, c, rec, tau + r_sub, pp->queries + (size_t)qid * 2 * W, r_sub);
 #else
-  bmih_append_impl<W>(pp, bv_qid[warp][qq], t, d, j, c, bv_qrec + warp * (kBmihQT * QS) + qq * QS, tau_s);
+  bmih_append_impl<W>(pp, qid, t, d, j, c, rec, tau);
 #endif
+}
+// the warp's n queued hits, 32 at a time (called by all lanes, n warp-uniform)
+template <int W, int QS>
+__device__ __noinline__ void bmih_drain_hits(const BmihParams* pp, uint32_t t, uint32_t a0, uint32_t n) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncwarp();
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t e = bv_hitq[warp][i];
+    bmih_process_hit<W, QS>(pp, t, a0 + (e >> 5), e & 31u);
+  }
+  __syncwarp();
 }
 
 // Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
 // item's queries in its slice of shared memory and streams the item's codes 32 lanes x C codes at a time.
+// The distance loop only FILTERS (one POPC per 64 bits when PREFILTER): a code that passes is queued in the warp's
+// hit queue - position and staged query - and the queue is worked off 32 hits at a time (bmih_drain_hits), so that the
+// exact re-check, the de-duplication and the append run with full lanes instead of one or two inside a divergent branch
+// of the loop.  The queue is filled by ballot (no atomics: the warp enters the rare path together when any lane has a hit)
+// and drained before it could overflow, so memory stays bounded whatever the data.
 template <int W, bool PREFILTER, int U4>
 __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY_CTAS : VC_VERIFY_CTAS_W2)) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
   using Cfg = BmihCfg<W, U4>;
   constexpr int C = Cfg::C, QS = Cfg::QS;
   constexpr int NW = kBmihThreads / 32;
   constexpr uint32_t WSTEP = 32 * C;                       // codes per warp step
-  __shared__ const uint64_t* s_codes[kMaxTables];          // table payload pointers, fetched once
-  __shared__ const uint32_t* s_ids[kMaxTables];
   __shared__ uint32_t s_cut_all[NW][kBmihQT];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < p.m) { s_codes[tid] = p.tables[tid].codes; s_ids[tid] = p.tables[tid].ids; }
+  if (tid < p.m) { bv_codes[tid] = p.tables[tid].codes; bv_ids[tid] = p.tables[tid].ids; }
+  if (tid < NW) bv_pairs[tid] = 0;
   __syncthreads();
   static_assert(QS <= kBmihQSMax, "staging area too small");
   uint32_t* s_qrec = bv_qrec + warp * (kBmihQT * QS);
@@ -337,27 +370,28 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
   // k-th id (the last step of a search, table 0 of radius 3 at 1 B codes, scans ~30 % of every bucket instead of all).
   const uint32_t lb = p.m * p.r_lo + p.t_begin;
   const uint32_t n_items = *p.n_items;
-  unsigned long long my_pairs = 0;                     // lane 0: tests executed by this warp
-  // lane 0 runs one item ahead: the claim (atomic) and the descriptor of the next item are fetched while the
-  // warp works on the current one
-  uint32_t next_it = n_items;
-  BmihItem nd = BmihItem{0, 0, 0, 0, 0};
-  if (lane == 0) {
-    next_it = atomicAdd(p.item_cursor, 1u);
-    if (next_it < n_items) nd = p.items[next_it];
-  }
+  uint32_t hitn = 0;                                   // entries in the warp's hit queue (warp-uniform)
+  // Work items are claimed two ahead, all in registers: the descriptor of the next item (one word per lane 0..4) and the
+  // claim of the one after it are in flight while the warp works on the current item, and are first touched at the top
+  // of the next iteration.
+  uint32_t claim = 0;
+  if (lane == 0) claim = atomicAdd(p.item_cursor, 1u);
+  uint32_t it_next = __shfl_sync(0xffffffffu, claim, 0);
+  uint32_t ndw = 0;
+  if (lane < 5 && it_next < n_items) ndw = reinterpret_cast<const uint32_t*>(p.items + it_next)[lane];
+  if (lane == 0) claim = atomicAdd(p.item_cursor, 1u);
   for (;;) {
-    const uint32_t it = __shfl_sync(0xffffffffu, next_it, 0);
+    const uint32_t it = it_next;
     if (it >= n_items) break;
-    const uint32_t t = __shfl_sync(0xffffffffu, nd.t, 0);
-    const uint32_t c0 = __shfl_sync(0xffffffffu, nd.c0, 0), c1 = __shfl_sync(0xffffffffu, nd.c1, 0);
-    const uint32_t qbeg = __shfl_sync(0xffffffffu, nd.qbeg, 0), qn = __shfl_sync(0xffffffffu, nd.qn, 0);
-    if (lane == 0) {
-      next_it = atomicAdd(p.item_cursor, 1u);
-      if (next_it < n_items) nd = p.items[next_it];
-    }
+    const uint32_t t = __shfl_sync(0xffffffffu, ndw, 0);
+    const uint32_t c0 = __shfl_sync(0xffffffffu, ndw, 1), c1 = __shfl_sync(0xffffffffu, ndw, 2);
+    const uint32_t qbeg = __shfl_sync(0xffffffffu, ndw, 3), qn = __shfl_sync(0xffffffffu, ndw, 4);
+    it_next = __shfl_sync(0xffffffffu, claim, 0);
+    ndw = 0;
+    if (lane < 5 && it_next < n_items) ndw = reinterpret_cast<const uint32_t*>(p.items + it_next)[lane];
+    if (lane == 0) claim = atomicAdd(p.item_cursor, 1u);
     const uint32_t a0 = W == 1 ? (c0 & ~1u) : c0;                      // 16-byte aligned start
-    const uint4* src = reinterpret_cast<const uint4*>(s_codes[t] + (size_t)a0 * W);
+    const uint4* src = reinterpret_cast<const uint4*>(bv_codes[t] + (size_t)a0 * W);
     const uint32_t u4_end = ((c1 - a0) * W + 1) / 2;                   // 16-byte units of the item
     const uint32_t u4_last = u4_end - 1;
     CodeRegs<W> code[C];
@@ -366,7 +400,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
 #pragma unroll
       for (int u = 0; u < U4; ++u) {
         // lanes past the end of the item re-read its last 16 bytes (no predicate, no zero fill): what they find is
-        // dropped by the range test in front of the append
+        // dropped by the range test in front of the hit queue
         uint4 v;
         if constexpr (W == 1) {
           const uint32_t idx = min(u4_base + u * 32 + lane, u4_last);
@@ -408,15 +442,15 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
     // Every code of the item has the bucket's key as its substring t, so that substring adds the same r_own = popc(query
     // substring ^ key) to every distance.  With the key written into the staged query the XOR is zero there: the one-POPC lower
     // bound no longer loses those 16 bits to the OR with their partner substring, and is tested against tau - r_own (a sharper
-    // filter at no cost per test: ~4 x fewer records on the slow path at radius 2).  The slow path adds r_own back and takes
-    // the query's own words for the first-discoverer test; a threshold below r_own is clamped to 0, which can only let codes
-    // through that the append path then handles with their true distance.
+    // filter at no cost per test: 128-bit codes at radius 4, tau = 36: 0.07 % instead of 0.4 % of the codes pass it).  The hit
+    // path adds r_own back and takes the query's own words for the first-discoverer test; a threshold below r_own is clamped
+    // to 0, which can only let codes through that the append path then handles with their true distance.
     static_assert(QS >= 2 * W + 2, "no spare word in the staged record");
     if (!p.scan_mode) {
       __syncwarp();
       if (lane < qn) {
         uint32_t* rec = s_qrec + lane * QS;
-        const uint32_t key = substring<W>(reinterpret_cast<const uint32_t*>(s_codes[t] + (size_t)c0 * W), t, p.sbits);
+        const uint32_t key = substring<W>(reinterpret_cast<const uint32_t*>(bv_codes[t] + (size_t)c0 * W), t, p.sbits);
         const uint32_t off = t * p.sbits, wi = off >> 5, sh = off & 31;
         const uint32_t mask = (p.sbits == 32 ? 0xFFFFFFFFu : ((1u << p.sbits) - 1u)) << sh;
         const uint32_t qw = rec[wi];
@@ -436,17 +470,18 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
     s_cut[lane] = my_cut;
     const bool use_cut = __any_sync(0xffffffffu, my_cut != 0xFFFFFFFFu);
     uint32_t qlive = qn;                               // staged queries still interested in the rest of the item
-    if (VC_PAIRS_PER_ITEM && !use_cut) my_pairs += (unsigned long long)(c1 - c0) * qn;   // no query leaves early: counted once
+    uint32_t item_pairs = use_cut ? 0u : (c1 - c0) * qn;       // tests of this item (no query leaves early: counted once; < 2^32: cpi * 32)
     __syncwarp();
     for (uint32_t base = a0; base < c1; base += WSTEP) {
       if (use_cut) {
         // queries whose k-th id lies at or before the first id of this step are done with the bucket: the staged list
         // is compacted (each query leaves once), the distance loop below stays dense
-        const uint32_t fid = __ldg(&s_ids[t][max(base, c0)]);
+        const uint32_t fid = __ldg(&bv_ids[t][max(base, c0)]);
         const bool keep = lane < qlive && s_cut[lane] > fid;
         const uint32_t alive = __ballot_sync(0xffffffffu, keep);
         if (!alive) break;
         if (alive != (qlive >= 32 ? 0xFFFFFFFFu : ((1u << qlive) - 1u))) {
+          if (VC_HIT_QUEUE && hitn) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }     // queued hits name staged slots: before they move
           uint32_t rec[QS];
 #pragma unroll
           for (int i = 0; i < QS; ++i) rec[i] = keep ? s_qrec[lane * QS + i] : 0u;
@@ -468,7 +503,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         const uint32_t ahead = (base - a0 + kPfDist * WSTEP) * W / 2;
         if (lane < 16 && ahead + lane * 8 < u4_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ahead + lane * 8));
       }
-      if (!VC_PAIRS_PER_ITEM || use_cut) my_pairs += (unsigned long long)(min(c1, base + WSTEP) - max(base, c0)) * qlive;
+      if (use_cut) item_pairs += (min(c1, base + WSTEP) - max(base, c0)) * qlive;
       // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
       // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
       // of the codes down the slow path.  The load is issued here and consumed after this step's math.
@@ -489,29 +524,40 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
 #pragma unroll
           for (int c = 0; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
         }
-        if (mn <= tau) {
-          uint32_t qq = q;
-          asm volatile("" : "+r"(qq));        // keeps the address arithmetic of this rare path out of the loop body
-          // the minimum did not say which code: groups of four are ruled out by their own minimum, then the cheap bound
-          // again per code (one POPC, not two, for the rest)
+#if VC_HIT_QUEUE
+        if (__any_sync(0xffffffffu, mn <= tau)) {
+          // some lane has a code that passes: the whole warp runs the filter again per code (on laundered query words, so
+          // that nothing computed for the common path has to stay alive for this one) and queues what passes by ballot
+          uint32_t qq = q, qw2[2 * W];
+          asm volatile("" : "+r"(qq));
 #pragma unroll
-          for (int g = 0; g < C; g += 4) {
-            if constexpr (PREFILTER && C > 4) {
-              uint32_t gm = hamming_lower_bound<W>(code[g].w, cur.qw);
+          for (int i = 0; i < 2 * W; ++i) { qw2[i] = cur.qw[i]; asm volatile("" : "+r"(qw2[i])); }
 #pragma unroll
-              for (int c = g + 1; c < g + 4 && c < C; ++c) gm = min(gm, hamming_lower_bound<W>(code[c].w, cur.qw));
-              if (gm > tau) continue;
-            }
-#pragma unroll
-            for (int c = g; c < g + 4 && c < C; ++c) {
-              if (!PREFILTER || hamming_lower_bound<W>(code[c].w, cur.qw) <= tau) {
-                const uint32_t d = hamming_exact<W>(code[c].w, cur.qw);
-                const uint32_t j = base + local_of(c);
-                if (d <= tau && j >= c0 && j < c1) bmih_append_staged<W, QS>(&p, qq, t, d, j, code[c], tau);
-              }
+          for (int c = 0; c < C; ++c) {
+            const uint32_t v = PREFILTER ? hamming_lower_bound<W>(code[c].w, qw2) : hamming_exact<W>(code[c].w, qw2);
+            const uint32_t j = base + local_of(c);
+            const bool hit = v <= tau && j >= c0 && j < c1;
+            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+            if (hm) {
+              if (hitn + 32u > (uint32_t)kBmihHitQ) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }
+              if (hit) bv_hitq[tid >> 5][hitn + __popc(hm & ((1u << lane) - 1u))] = ((j - a0) << 5) | qq;
+              hitn += __popc(hm);
             }
           }
         }
+#else
+        if (mn <= tau) {
+          uint32_t qq = q;
+          asm volatile("" : "+r"(qq));        // keeps the address arithmetic of this rare path out of the loop body
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if ((PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw)) <= tau) {
+              const uint32_t j = base + local_of(c);
+              if (j >= c0 && j < c1) bmih_process_hit<W, QS>(&p, t, j, qq);
+            }
+          }
+        }
+#endif
       };
       // two records in flight, ping-pong: the next record's LDS overlaps this record's math, without register moves
       QRec<W> ra = load_qrec<W, QS>(s_qrec, 0), rb;
@@ -524,22 +570,26 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
           test_query(rb, q + 1);
         }
       }
+      __syncwarp();
       if (refresh) {
-        __syncwarp();
 #if VC_KEY_SUBST
         if (lane < qlive) {
           const uint32_t r_own = s_qrec[lane * QS + 2 * W + 1];
           const uint32_t ft = fresh_tau >= r_own ? fresh_tau - r_own : 0u;
-          if (ft < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = ft;
+          if (ft < s_qrec[lane * QS + 2 * W]) atomicMin(&s_qrec[lane * QS + 2 * W], ft);
         }
 #else
-        if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) s_qrec[lane * QS + 2 * W] = fresh_tau;
+        if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) atomicMin(&s_qrec[lane * QS + 2 * W], fresh_tau);
 #endif
         __syncwarp();
       }
+      // hits of this step: worked off once a warp's worth has gathered, and before the item (its staged queries) is left
+      if (VC_HIT_QUEUE && (hitn >= 32u || (hitn && base + WSTEP >= c1))) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }
     }
+    if (VC_HIT_QUEUE && hitn) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }      // the id cut left the loop early
+    if (lane == 0) bv_pairs[warp] += item_pairs;
   }
-  if (lane == 0 && p.exec_pairs && my_pairs) atomicAdd(p.exec_pairs, my_pairs);
+  if (lane == 0 && p.exec_pairs && bv_pairs[warp]) atomicAdd(p.exec_pairs, bv_pairs[warp]);
 }
 
 // ---- 4. settle: per query after a step --------------------------------------------------------------------
@@ -548,20 +598,43 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
 // summed over all id-shards (GPUs) by the caller's all-reduce.
 template <int W>
 __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, uint32_t* xhist) {
-  __shared__ uint64_t buf[kBmihCap];
+  __shared__ uint64_t buf[kBmihSort];
   __shared__ uint32_t cnt;
+  __shared__ uint64_t s_tau;
   constexpr int HB = BmihCfg<W>::HB;
   const uint32_t tid = threadIdx.x;
   if (blockIdx.x >= n_list) return;
   const uint32_t q = list[blockIdx.x];
   const uint32_t raw = p.gcnt[q];
-  const uint32_t n = min(raw, (uint32_t)kBmihCap);
-  for (uint32_t i = tid; i < n; i += 256) buf[i] = p.gbuf[(size_t)q * kBmihCap + i];
-  if (tid == 0) cnt = n;
-  __syncthreads();
-  const uint64_t tk = topk_compact(buf, &cnt, kBmihCap, p.k, tid, 256, BlockSync());
+  const uint32_t n = min(raw, p.cap);
+  uint64_t* gb = p.gbuf + (size_t)q * p.cap;
+  uint64_t tk;
+  if (n <= (uint32_t)kBmihSort) {
+    for (uint32_t i = tid; i < n; i += 256) buf[i] = gb[i];
+    if (tid == 0) cnt = n;
+    __syncthreads();
+    tk = topk_compact(buf, &cnt, kBmihSort, p.k, tid, 256, BlockSync());
+  } else {
+    // more candidates than fit in shared memory (large k): folded in 256 at a time, the buffer compacted to its k best
+    // whenever the next 256 might not fit; entries that no longer beat the running k-th key are dropped on the way in
+    if (tid == 0) { cnt = 0; s_tau = kEmptyKey; }
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += 256) {
+      if (cnt + 256 > (uint32_t)kBmihSort) {                   // uniform: cnt is stable between barriers
+        const uint64_t t2 = topk_compact(buf, &cnt, kBmihSort, p.k, tid, 256, BlockSync());
+        if (tid == 0) s_tau = t2;
+        __syncthreads();
+      }
+      if (base + tid < n) {
+        const uint64_t key = gb[base + tid];
+        if (key < s_tau) buf[atomicAdd(&cnt, 1u)] = key;
+      }
+      __syncthreads();
+    }
+    tk = topk_compact(buf, &cnt, kBmihSort, p.k, tid, 256, BlockSync());
+  }
   const uint32_t kept = cnt;
-  for (uint32_t i = tid; i < kept; i += 256) p.gbuf[(size_t)q * kBmihCap + i] = buf[i];
+  for (uint32_t i = tid; i < kept; i += 256) gb[i] = buf[i];
   // per-distance histogram of what is kept -> xhist (for the decide kernel / the cross-shard sum); its prefix
   // sums -> ghist (the cumulative counts the append path maintains)
   __shared__ uint32_t sh[HB];
@@ -569,11 +642,15 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   __syncthreads();
   for (uint32_t i = tid; i < kept; i += 256) atomicAdd(&sh[(uint32_t)(buf[i] >> 32)], 1u);
   __syncthreads();
+  // the last bin is not a distance (distances end at 64 W): it carries "this query's buffer overflowed on this shard", so
+  // that after the cross-shard sum every shard takes the query out of the batched search at the same step (bmih_decide_kernel)
+  if (tid == 0) sh[HB - 1] = p.gflag[q] & 1u;
+  __syncthreads();
   for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = sh[i];
   if (tid == 0) {
     uint32_t* gc = p.ghist + (size_t)q * HB;
     uint32_t cum = 0;
-    for (uint32_t d = 0; d < HB; ++d) { cum += sh[d]; gc[d] = cum; }
+    for (uint32_t d = 0; d <= 64 * W; ++d) { cum += sh[d]; gc[d] = cum; }
   }
   if (tid == 0) {
     p.gcnt[q] = kept;
@@ -613,7 +690,9 @@ __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uin
   p.gradius[q] = r;
   for (uint32_t rr = p.r_lo; rr <= r; ++rr)
     p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][rr];    // n_sub_reads_ of this step
-  if (p.gflag[q] & 1u) *any_overflow = 1;                                                // buffer overflowed: redone by the per-query kernel
+  // candidate buffer overflowed (here or, id-sharded, on any shard: the flag bin is part of the summed histogram): the query
+  // leaves the batched search now - on every shard at the same step - and is answered by the per-query kernel afterwards
+  if (xhist[(size_t)q * HB + HB - 1]) { atomicOr(&p.gflag[q], 1u); *any_overflow = 1; stop = true; }
   // would this query stop somewhere inside the next radius even if tau did not improve any more?
   if (!stop && level_done && tau != kInfDist && tau + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
   if (stop) atomicOr(&p.gflag[q], 2u);
@@ -638,7 +717,7 @@ __global__ void bmih_idhist_kernel(const BmihParams p, const uint32_t* list, uin
   uint32_t* row = idh + (size_t)q * (kIdBins + 1);
   const uint32_t n = min(p.gcnt[q], p.k);
   for (uint32_t i = lane; i < n; i += 32) {
-    const uint64_t key = p.gbuf[(size_t)q * kBmihCap + i];
+    const uint64_t key = p.gbuf[(size_t)q * p.cap + i];
     const uint32_t d = (uint32_t)(key >> 32);
     if (d < tau) atomicAdd(&row[0], 1u);
     else if (d == tau) atomicAdd(&row[1 + ((uint32_t)key >> 24)], 1u);
@@ -812,7 +891,7 @@ __global__ void __launch_bounds__(256) scan_bootstrap_kernel(const BmihParams p,
 __global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_query_stats* stats) {
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t kept = min(p.gcnt[q], p.k);
-  for (uint32_t i = tid; i < p.k; i += blockDim.x) out_keys[(size_t)q * p.k + i] = i < kept ? p.gbuf[(size_t)q * kBmihCap + i] : kEmptyKey;
+  for (uint32_t i = tid; i < p.k; i += blockDim.x) out_keys[(size_t)q * p.k + i] = i < kept ? p.gbuf[(size_t)q * p.cap + i] : kEmptyKey;
   if (stats && tid == 0) {
     vc_query_stats st;
     st.radius = p.gradius[q]; st.n_results = kept; st.probes = p.gprobes[q]; st.occupancy_tests = 0;
@@ -821,13 +900,10 @@ __global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_qu
   }
 }
 
-// overflowed queries take their answer from the per-query kernel's output
-__global__ void bmih_patch_kernel(const uint32_t* gflag, uint32_t k, const uint64_t* redo_keys, const vc_query_stats* redo_stats,
-                                  uint64_t* out_keys, vc_query_stats* stats) {
-  const uint32_t q = blockIdx.x;
-  if (!(gflag[q] & 1u)) return;
-  for (uint32_t i = threadIdx.x; i < k; i += blockDim.x) out_keys[(size_t)q * k + i] = redo_keys[(size_t)q * k + i];
-  if (stats && redo_stats && threadIdx.x == 0) stats[q] = redo_stats[q];
+// queries whose candidate buffer overflowed: listed for the per-query kernel, which writes their rows of the output itself
+__global__ void bmih_redo_list_kernel(const uint32_t* gflag, uint32_t nq, uint32_t* list, uint32_t* n_list) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && (gflag[q] & 1u)) list[atomicAdd(n_list, 1u)] = q;
 }
 
 }  // namespace vc

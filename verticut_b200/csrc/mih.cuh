@@ -43,6 +43,7 @@ struct MihParams {
   int max_radius;            // >= 0: fixed radius; < 0: stop rule
   int table_steps;           // exact mode: 1 = test the stop rule after every table of a radius (d_k <= m*r + t), 0 = per radius
   const TableDev* tables;    // [m] in device memory
+  const uint32_t* qsel;      // null: CTA b answers query b; else CTA b answers query qsel[b] (rows of queries / out_keys / stats are indexed by query)
   uint64_t* out_keys;        // [nq][k]
   vc_query_stats* stats;     // [nq] or null
 };
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(kMihThreads, 3) mih_search_kernel(const MihPar
   __shared__ uint32_t s_hist[64 * W + 32];      // distances of the distinct candidates that passed the threshold
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t q = blockIdx.x;
+  const uint32_t q = p.qsel ? p.qsel[blockIdx.x] : blockIdx.x;
   const uint32_t m = p.m, sbits = p.sbits, k = p.k;
 
   if (tid < 2 * W) s_q[tid] = p.queries[(size_t)q * 2 * W + tid];

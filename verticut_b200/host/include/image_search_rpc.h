@@ -138,11 +138,13 @@ inline bool send_all(int fd, const std::string& s) {
   return true;
 }
 // appends what arrives to buf until one whole MessagePack object sits at its front; 1 = got one, 0 = peer closed, -1 = error
-inline int recv_object(int fd, std::string& buf, mp::Value& out, size_t max_bytes) {
+// max_bytes / max_items bound what one message may cost: the buffer is re-parsed after every recv(), which is O(max_items)
+// per attempt (strings are length-checked before they are copied), and the decoder never allocates more than max_items values.
+inline int recv_object(int fd, std::string& buf, mp::Value& out, size_t max_bytes, size_t max_items = (size_t)1 << 20) {
   for (;;) {
     if (!buf.empty()) {
       size_t used = 0;
-      const mp::ParseStatus st = mp::parse(buf.data(), buf.size(), used, out);
+      const mp::ParseStatus st = mp::parse(buf.data(), buf.size(), used, out, max_items);
       if (st == mp::PARSE_OK) { buf.erase(0, used); return 1; }
       if (st == mp::PARSE_ERROR || buf.size() > max_bytes) return -1;
     }
@@ -207,7 +209,7 @@ class image_search_server {
       { std::lock_guard<std::mutex> g(mu_); conns_.insert(fd); }
       std::string buf;
       mp::Value msg;
-      while (!stop_ && detail::recv_object(fd, buf, msg, kMaxMessage) == 1) {
+      while (!stop_ && detail::recv_object(fd, buf, msg, kMaxMessage, kMaxItems) == 1) {
         const std::string reply = handle_message(*svc_, msg);
         if (!reply.empty() && !detail::send_all(fd, reply)) break;
       }
@@ -215,7 +217,9 @@ class image_search_server {
       ::close(fd);
     }
   }
-  static const size_t kMaxMessage = 1u << 20;   // requests are tens of bytes; a peer that streams more without completing an object is dropped
+  static const size_t kMaxMessage = 1u << 20;   // requests are tens of bytes (a ping may carry a long string); a peer that streams more without completing an object is dropped
+  static const size_t kMaxItems = 16;           // [type, msgid, method, [id, knn, approximate]] = 7 items: the decoder never allocates more, and an
+                                                // incomplete message costs O(1) to re-parse after each recv() (a string's length prefix is checked first)
   service* svc_;
   int lfd_;
   int port_;

@@ -83,7 +83,9 @@ enum ParseStatus { PARSE_OK = 0, PARSE_NEED_MORE = 1, PARSE_ERROR = 2 };
 namespace detail {
 inline uint64_t rd(const uint8_t* p, int n) { uint64_t v = 0; for (int i = 0; i < n; ++i) v = (v << 8) | p[i]; return v; }
 
-inline ParseStatus parse_at(const uint8_t* p, size_t n, size_t& pos, Value& v, int depth) {
+// `budget`: array / map items the whole message may still declare.  A Value is ~100 bytes, so without it a 1 MB message of
+// one-byte items would cost ~100 MB per connection to decode; the callers pass what their interface can need.
+inline ParseStatus parse_at(const uint8_t* p, size_t n, size_t& pos, Value& v, int depth, size_t& budget) {
   if (depth > 32) return PARSE_ERROR;                       // nothing on this interface nests deeper than 4
   if (pos >= n) return PARSE_NEED_MORE;
   const uint8_t t = p[pos++];
@@ -93,9 +95,11 @@ inline ParseStatus parse_at(const uint8_t* p, size_t n, size_t& pos, Value& v, i
     v.type = ty; v.s.assign((const char*)p + pos, len); pos += len; return PARSE_OK;
   };
   auto items = [&](size_t cnt, Value::Type ty) -> ParseStatus {
+    if (cnt > budget) return PARSE_ERROR;                   // more items than the interface ever sends
+    budget -= cnt;
     if (cnt > n - pos) return PARSE_NEED_MORE;              // every item takes at least one byte: bounds the allocation
     v.type = ty; v.a.clear(); v.a.resize(cnt);
-    for (size_t k = 0; k < cnt; ++k) { ParseStatus st = parse_at(p, n, pos, v.a[k], depth + 1); if (st != PARSE_OK) return st; }
+    for (size_t k = 0; k < cnt; ++k) { ParseStatus st = parse_at(p, n, pos, v.a[k], depth + 1, budget); if (st != PARSE_OK) return st; }
     return PARSE_OK;
   };
   auto lenpfx = [&](int k, uint64_t& len) -> bool { if (!need((size_t)k)) return false; len = rd(p + pos, k); pos += k; return true; };
@@ -141,9 +145,9 @@ inline ParseStatus parse_at(const uint8_t* p, size_t n, size_t& pos, Value& v, i
 
 // One object from the front of [p, p + n).  PARSE_OK: `consumed` bytes were used.  PARSE_NEED_MORE: the object is
 // not complete yet (call again with more bytes).  PARSE_ERROR: not MessagePack.
-inline ParseStatus parse(const void* p, size_t n, size_t& consumed, Value& out) {
-  size_t pos = 0;
-  const ParseStatus st = detail::parse_at((const uint8_t*)p, n, pos, out, 0);
+inline ParseStatus parse(const void* p, size_t n, size_t& consumed, Value& out, size_t max_items = (size_t)1 << 20) {
+  size_t pos = 0, budget = max_items;
+  const ParseStatus st = detail::parse_at((const uint8_t*)p, n, pos, out, 0, budget);
   consumed = st == PARSE_OK ? pos : 0;
   return st;
 }

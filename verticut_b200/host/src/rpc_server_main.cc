@@ -49,6 +49,9 @@ static void usage() {
 struct gpu_service : vcrpc::service {
   explicit gpu_service(GpuTableProxy* proxy) : client(proxy) {}
   vcrpc::result_list search_image_by_id(uint32_t id, uint32_t knn, bool approximate) {
+    // knn comes off the wire as a uint32: 0, > VC_MAX_K or >= 2^31 must not reach the library (one bad request would
+    // otherwise take down the process that holds the only copy of the GPU index); the exception becomes the call's error
+    if (knn == 0 || knn > (uint32_t)VC_MAX_K) throw std::runtime_error("knn must be in [1, " + std::to_string(VC_MAX_K) + "]");
     std::lock_guard<std::mutex> g(mu);
     vcrpc::result_list r = client.search_image_by_id(id, (int)knn, approximate);
     printf("finish query for %u\n", id);          // src/image_search_server.cc:82
