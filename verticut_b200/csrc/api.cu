@@ -142,6 +142,8 @@ struct vc_index {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
   cudaEvent_t lev[2 * 34] = {nullptr};   // batched MIH: one (start, stop) pair per radius level around the verify kernel
+  cudaEvent_t lev_x[2 * 34] = {nullptr}; // ... and (step begin, step end): probes + work items before the verify kernel, settle + exchange + decide after it
+  cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr;   // whole batched search (first launch .. finish kernel)
   int lev_used = 0;                        // > 0: last search was batched, sum these pairs
   std::vector<int64_t> step_exec;     // ... and the tests the verify kernel really executed
   std::vector<int64_t> step_codes, step_pairs;   // per step of the last batched search: codes of distinct probed buckets, code-query tests
@@ -228,6 +230,8 @@ void vc_index_destroy(vc_index* ix) {
   if (ix->d_codes) cudaFree(ix->d_codes);
   if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
   for (cudaEvent_t e : ix->lev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ix->lev_x) if (e) cudaEventDestroy(e);
+  if (ix->ev_s0) { cudaEventDestroy(ix->ev_s0); cudaEventDestroy(ix->ev_s1); }
   DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate,
                    &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_redo, &ix->b_idh, &ix->b_trace};
   for (DevBuf* b : db) b->release();
@@ -988,6 +992,9 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     const uint64_t avg = (ix->n >> sbits) + 1;
     const uint64_t steps = std::min<uint64_t>(8, std::max<uint64_t>(2, (avg + Cfg::STEP - 1) / Cfg::STEP));
     p.cpi = ix->mih_cpi_steps > 0 ? (uint32_t)ix->mih_cpi_steps * Cfg::STEP : (uint32_t)steps * Cfg::STEP;
+    // 64-bit codes are loaded in pairs from an even position: an item that starts at an odd one is one code longer for the
+    // kernel, and its hit queue numbers at most 64 warp steps (of 256 codes) per item
+    if (W == 1) p.cpi -= 2;
   }
   // long buckets: 16 codes per thread per step (less loop overhead per pair); short ones: 8
   const bool wide = ix->mih_wide > 0;   // measured slower than the 8-codes-per-thread variant at 3 CTAs/SM; kept as a knob
@@ -1024,6 +1031,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     ix->launches++;
   }
   // ---- start: all queries active, thresholds bootstrapped from a sample of each query's own buckets -------
+  if (ix->profile) {
+    if (!ix->ev_s0) { CU(cudaEventCreate(&ix->ev_s0)); CU(cudaEventCreate(&ix->ev_s1)); }
+    cudaEventRecord(ix->ev_s0, st);
+  }
   CU(cudaMemsetAsync(ctr, 0, 128, st));
   CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));      // histograms count this search's candidates only
   CU(cudaMemsetAsync(xhist, 0, (size_t)nq * Cfg::HB * 4, st));
@@ -1055,6 +1066,14 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     const uint32_t r_lo = r;
     if (r == 0 && !granular && ix->mih_table_steps < 0 && sbits >= 1 && max_radius != 0) r = 1;
     p.radius = r; p.r_lo = r_lo; p.t_begin = t0; p.t_end = t1; p.active = cur; p.n_active = n_active; p.next_active = nxt;
+    const bool timed = ix->profile && levels < 34;
+    if (timed) {
+      if (!ix->lev[2 * levels]) {
+        CU(cudaEventCreate(&ix->lev[2 * levels])); CU(cudaEventCreate(&ix->lev[2 * levels + 1]));
+        CU(cudaEventCreate(&ix->lev_x[2 * levels])); CU(cudaEventCreate(&ix->lev_x[2 * levels + 1]));
+      }
+      cudaEventRecord(ix->lev_x[2 * levels], st);
+    }
     uint64_t per_table_probes = 0;
     for (uint32_t rr = r_lo; rr <= r; ++rr) per_table_probes += host_binom(sbits, rr);
     const uint64_t total_probes = (uint64_t)n_active * (t1 - t0) * per_table_probes;
@@ -1122,11 +1141,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     CU(cudaMemsetAsync(ctr + 4, 0, 4, st));
     p.count_in_write = single_pass ? 1u : 0u;
     bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
-    const bool timed = ix->profile && levels < 34;
-    if (timed) {
-      if (!ix->lev[2 * levels]) { CU(cudaEventCreate(&ix->lev[2 * levels])); CU(cudaEventCreate(&ix->lev[2 * levels + 1])); }
-      cudaEventRecord(ix->lev[2 * levels], st);
-    }
+    if (timed) cudaEventRecord(ix->lev[2 * levels], st);
     // few queries per probed bucket (radii 0 and 1): the step is not POPC-bound, and the exact distance as the filter sends
     // far fewer codes down the slow path than the one-POPC lower bound does (4.22 -> 4.05 ms at 1 B codes, batch 4096)
     const bool pf_auto = ix->mih_prefilter < 0;
@@ -1144,6 +1159,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       if (ix->allreduce_fn(ix->allreduce_user, xhist, (uint64_t)nq * Cfg::HB, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
     }
     bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
+    if (timed) cudaEventRecord(ix->lev_x[2 * levels + 1], st);
     ix->launches += single_pass ? 6 : 7;
     CU(cudaGetLastError());
     uint32_t h5[14];
@@ -1187,6 +1203,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   (void)first_verify;
   bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, d_stats);
   ix->launches++;
+  if (ix->profile) cudaEventRecord(ix->ev_s1, st);
   if (h_ctr[3]) {
     // some candidate buffers overflowed (heavy ties): those queries - and only those - take the per-query kernel's exact answer
     if ((rc = ix->b_redo.ensure((size_t)nq * 4 + 256))) return rc;
@@ -1335,7 +1352,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.batched")) ix->mih_batched = value;
   else if (!strcmp(name, "mih.prefilter")) ix->mih_prefilter = value;
   else if (!strcmp(name, "mih.cpi_steps")) {
-    if (value < 0 || value > 1024) return fail(VC_ERR_ARG, "mih.cpi_steps must be in [0, 1024]");     // the hit queue packs (position in the item) << 5
+    if (value < 0 || value > 8) return fail(VC_ERR_ARG, "mih.cpi_steps must be in [0, 8]");     // the hit queue packs the warp step of the item into 6 bits
     ix->mih_cpi_steps = value;
   }
   else if (!strcmp(name, "mih.wide")) ix->mih_wide = value;
@@ -1402,6 +1419,27 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
       CU(cudaEventElapsedTime(&ms, ix->lev[2 * i], ix->lev[2 * i + 1]));
       *value = (int64_t)((double)ms * 1e6);
     }
+  }
+  else if (!strncmp(name, "mih.step_pre_ns.", 16) || !strncmp(name, "mih.step_post_ns.", 17)) {
+    // the rest of a search step (profile = 1): begin of the step .. verify kernel (probes, counting sort, work items), and
+    // verify kernel .. end of the step (settle, the cross-shard exchange, decide)
+    const bool pre = name[10] == 'r';
+    const int i = atoi(name + (pre ? 16 : 17));
+    if (!ix->profile || i < 0 || i >= ix->lev_used) return fail(VC_ERR_STATE, "profiling is off or step out of range");
+    DeviceGuard g(ix->device);
+    float ms = 0.f;
+    CU(cudaEventSynchronize(ix->lev_x[2 * i + 1]));
+    if (pre) CU(cudaEventElapsedTime(&ms, ix->lev_x[2 * i], ix->lev[2 * i]));
+    else CU(cudaEventElapsedTime(&ms, ix->lev[2 * i + 1], ix->lev_x[2 * i + 1]));
+    *value = (int64_t)((double)ms * 1e6);
+  }
+  else if (!strcmp(name, "mih.search_ns")) {
+    if (!ix->profile || !ix->ev_s0 || ix->lev_used <= 0) return fail(VC_ERR_STATE, "profiling is off or the last search was not batched");
+    DeviceGuard g(ix->device);
+    float ms = 0.f;
+    CU(cudaEventSynchronize(ix->ev_s1));
+    CU(cudaEventElapsedTime(&ms, ix->ev_s0, ix->ev_s1));
+    *value = (int64_t)((double)ms * 1e6);
   }
   else if (!strcmp(name, "profile")) *value = ix->profile;
   else if (!strcmp(name, "last_kernel_ns")) {

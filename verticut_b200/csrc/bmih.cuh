@@ -36,7 +36,7 @@ constexpr int kBmihThreads = VC_BMIH_THREADS;
 constexpr int kBmihQT = 32;          // queries per work item
 constexpr int kBmihSort = 4096;      // entries the settle kernel sorts at a time (shared memory); k must stay below half of it
 constexpr int kBmihCapMin = 4096;    // candidate-buffer entries per query: at least this, see bmih_cap_for
-constexpr int kBmihHitQ = 128;       // deferred hits per warp of the verify kernel (bv_hitq)
+constexpr int kBmihHitQ = 32 * kBmihQT + 32;   // deferred hits per warp of the verify kernel (bv_hitq): what one warp step can add, plus an undrained rest
 constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (short-bucket variant)
 #ifndef VC_VERIFY_CTAS
 #define VC_VERIFY_CTAS 4   // 64-bit codes: 4 CTAs (32 warps, 64 registers) per SM - the kernel is latency-bound, 15.5 instead of 16.7 ms per search
@@ -302,22 +302,18 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
 constexpr int kBmihQSMax = 12;                                      // BmihCfg<4>::QS
 __shared__ __align__(16) uint32_t bv_qrec[(kBmihThreads / 32) * kBmihQT * kBmihQSMax];
 __shared__ uint32_t bv_qid[kBmihThreads / 32][kBmihQT];
-__shared__ uint32_t bv_hitq[kBmihThreads / 32][kBmihHitQ];          // deferred hits: (code position - item start) << 5 | staged query slot
+__shared__ uint16_t bv_hitq[kBmihThreads / 32][kBmihHitQ];          // deferred hits: warp step of the item << 10 | lane << 5 | staged query slot
+__shared__ uint32_t bv_hitn[kBmihThreads / 32];
 __shared__ unsigned long long bv_pairs[kBmihThreads / 32];          // tests executed by the warp (statistics)
 __shared__ const uint64_t* bv_codes[kMaxTables];                    // table payload pointers, fetched once per CTA
 __shared__ const uint32_t* bv_ids[kMaxTables];
 
-// One code (position j of table t, bucket order) that passed the filter for staged query qq of this warp: the exact distance
-// against the staged record, and - for the few that really beat the threshold - de-duplication and append.  The code is read
-// again from global memory (it was streamed through this SM a moment ago: an L2 hit).
+// One code (position j of table t, bucket order) of a queued hit against staged query qq of this warp: the exact distance
+// against the staged record, and - for the few that really beat the threshold - de-duplication and append.
 template <int W, int QS>
-__device__ __forceinline__ void bmih_process_hit(const BmihParams* pp, uint32_t t, uint32_t j, uint32_t qq) {
+__device__ __noinline__ void bmih_check_code(const BmihParams* pp, uint32_t t, uint32_t j, uint32_t qq, CodeRegs<W> c) {
   const uint32_t warp = threadIdx.x >> 5;
   uint32_t* rec = bv_qrec + warp * (kBmihQT * QS) + qq * QS;
-  CodeRegs<W> c;
-  const uint2* src = reinterpret_cast<const uint2*>(bv_codes[t] + (size_t)j * W);
-#pragma unroll
-  for (int i = 0; i < W; ++i) { const uint2 v = __ldg(src + i); c.w[2 * i] = v.x; c.w[2 * i + 1] = v.y; }
   const uint32_t tau = *(volatile uint32_t*)&rec[2 * W];
   const uint32_t d = hamming_exact<W>(c.w, rec);
   if (d > tau) return;
@@ -330,25 +326,57 @@ __device__ __forceinline__ void bmih_process_hit(const BmihParams* pp, uint32_t 
   bmih_append_impl<W>(pp, qid, t, d, j, c, rec, tau);
 #endif
 }
-// the warp's n queued hits, 32 at a time (called by all lanes, n warp-uniform)
-template <int W, int QS>
-__device__ __noinline__ void bmih_drain_hits(const BmihParams* pp, uint32_t t, uint32_t a0, uint32_t n) {
+// The warp's n queued hits, 32 at a time (called by all lanes, n warp-uniform).  A hit names a warp step of the item, a lane
+// and a staged query: "one of the C codes that lane held in that step passed the filter for that query".  The draining lane
+// reads those C codes again (they were streamed through this SM a moment ago: L2 hits, same addresses as bmih_verify_kernel's
+// load_step) and checks each exactly - so the distance loop itself never has to find out which code it was.
+template <int W, int U4, int QS>
+__device__ __noinline__ void bmih_drain_hits(const BmihParams* pp, uint32_t t, uint32_t a0, uint32_t c0, uint32_t c1, uint32_t n) {
+  constexpr int C = 2 * U4 / W;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint4* src = reinterpret_cast<const uint4*>(bv_codes[t] + (size_t)a0 * W);
+  const uint32_t u4_last = ((c1 - a0) * W + 1) / 2 - 1;
   __syncwarp();
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t e = bv_hitq[warp][i];
-    bmih_process_hit<W, QS>(pp, t, a0 + (e >> 5), e & 31u);
+    const uint32_t step = e >> 10, ln = (e >> 5) & 31u, qq = e & 31u;
+    const uint32_t base = a0 + step * (32 * C);
+    const uint32_t u4_base = (base - a0) * W / 2;
+    CodeRegs<W> code[C];
+#pragma unroll
+    for (int u = 0; u < U4; ++u) {
+      uint4 v;
+      if constexpr (W == 1) {
+        v = __ldg(src + min(u4_base + u * 32 + ln, u4_last));
+        code[2 * u].w[0] = v.x; code[2 * u].w[1] = v.y; code[2 * u + 1].w[0] = v.z; code[2 * u + 1].w[1] = v.w;
+      } else if constexpr (W == 2) {
+        v = __ldg(src + min(u4_base + u * 32 + ln, u4_last));
+        code[u].w[0] = v.x; code[u].w[1] = v.y; code[u].w[2] = v.z; code[u].w[3] = v.w;
+      } else {
+        const int cc = u / 2, h = u % 2;
+        v = __ldg(src + min(u4_base + 2 * (cc * 32 + ln), u4_last - 1) + h);
+        code[cc].w[4 * h + 0] = v.x; code[cc].w[4 * h + 1] = v.y; code[cc].w[4 * h + 2] = v.z; code[cc].w[4 * h + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const uint32_t j = base + (W == 1 ? 2 * ((c / 2) * 32 + ln) + (c & 1) : c * 32 + ln);
+      if (j >= c0 && j < c1) bmih_check_code<W, QS>(pp, t, j, qq, code[c]);
+    }
   }
+  __syncwarp();
+  if (lane == 0) bv_hitn[warp] = 0;
   __syncwarp();
 }
 
 // Warp-granular: every warp of the persistent grid pulls its own work items (no block barriers), keeps the
 // item's queries in its slice of shared memory and streams the item's codes 32 lanes x C codes at a time.
-// The distance loop only FILTERS (one POPC per 64 bits when PREFILTER): a code that passes is queued in the warp's
-// hit queue - position and staged query - and the queue is worked off 32 hits at a time (bmih_drain_hits), so that the
-// exact re-check, the de-duplication and the append run with full lanes instead of one or two inside a divergent branch
-// of the loop.  The queue is filled by ballot (no atomics: the warp enters the rare path together when any lane has a hit)
-// and drained before it could overflow, so memory stays bounded whatever the data.
+// The distance loop only FILTERS (one POPC per 64 bits when PREFILTER) the C codes a lane holds against one staged query; a
+// lane whose minimum passes pushes one 16-bit word - (warp step, lane, staged query) - onto the warp's hit queue and moves on:
+// no POPC, no call and no per-code work inside the divergent branch (the POPC pipe is what bounds this kernel, and a warp
+// instruction costs it the same with one active lane as with 32).  The queue is worked off 32 hits at a time
+// (bmih_drain_hits: exact re-check of those C codes, de-duplication, append - with full lanes), once a warp's worth has
+// gathered and before the item is left; it holds what a whole warp step can add, so memory stays bounded whatever the data.
 template <int W, bool PREFILTER, int U4>
 __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY_CTAS : VC_VERIFY_CTAS_W2)) bmih_verify_kernel(const __grid_constant__ BmihParams p) {
   using Cfg = BmihCfg<W, U4>;
@@ -358,7 +386,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
   __shared__ uint32_t s_cut_all[NW][kBmihQT];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < p.m) { bv_codes[tid] = p.tables[tid].codes; bv_ids[tid] = p.tables[tid].ids; }
-  if (tid < NW) bv_pairs[tid] = 0;
+  if (tid < NW) { bv_pairs[tid] = 0; bv_hitn[tid] = 0; }
   __syncthreads();
   static_assert(QS <= kBmihQSMax, "staging area too small");
   uint32_t* s_qrec = bv_qrec + warp * (kBmihQT * QS);
@@ -370,7 +398,6 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
   // k-th id (the last step of a search, table 0 of radius 3 at 1 B codes, scans ~30 % of every bucket instead of all).
   const uint32_t lb = p.m * p.r_lo + p.t_begin;
   const uint32_t n_items = *p.n_items;
-  uint32_t hitn = 0;                                   // entries in the warp's hit queue (warp-uniform)
   // Work items are claimed two ahead, all in registers: the descriptor of the next item (one word per lane 0..4) and the
   // claim of the one after it are in flight while the warp works on the current item, and are first touched at the top
   // of the next iteration.
@@ -481,7 +508,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         const uint32_t alive = __ballot_sync(0xffffffffu, keep);
         if (!alive) break;
         if (alive != (qlive >= 32 ? 0xFFFFFFFFu : ((1u << qlive) - 1u))) {
-          if (VC_HIT_QUEUE && hitn) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }     // queued hits name staged slots: before they move
+          if (VC_HIT_QUEUE && bv_hitn[warp]) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1, bv_hitn[warp]);     // queued hits name staged slots: before they move
           uint32_t rec[QS];
 #pragma unroll
           for (int i = 0; i < QS; ++i) rec[i] = keep ? s_qrec[lane * QS + i] : 0u;
@@ -512,6 +539,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       if (refresh && lane < qlive) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
       // one staged query against this thread's C codes: the minimum of the (lower-bound) distances decides; the rare
       // hit recomputes per code
+      const uint32_t stepq = (((base - a0) / WSTEP) << 10) | (lane << 5);      // this lane's hit-queue word, without the query slot
       auto test_query = [&](const QRec<W>& cur, uint32_t q) {
         const uint32_t tau = cur.tau;
         uint32_t mn;
@@ -525,26 +553,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
           for (int c = 0; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
         }
 #if VC_HIT_QUEUE
-        if (__any_sync(0xffffffffu, mn <= tau)) {
-          // some lane has a code that passes: the whole warp runs the filter again per code (on laundered query words, so
-          // that nothing computed for the common path has to stay alive for this one) and queues what passes by ballot
-          uint32_t qq = q, qw2[2 * W];
-          asm volatile("" : "+r"(qq));
-#pragma unroll
-          for (int i = 0; i < 2 * W; ++i) { qw2[i] = cur.qw[i]; asm volatile("" : "+r"(qw2[i])); }
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const uint32_t v = PREFILTER ? hamming_lower_bound<W>(code[c].w, qw2) : hamming_exact<W>(code[c].w, qw2);
-            const uint32_t j = base + local_of(c);
-            const bool hit = v <= tau && j >= c0 && j < c1;
-            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
-            if (hm) {
-              if (hitn + 32u > (uint32_t)kBmihHitQ) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }
-              if (hit) bv_hitq[tid >> 5][hitn + __popc(hm & ((1u << lane) - 1u))] = ((j - a0) << 5) | qq;
-              hitn += __popc(hm);
-            }
-          }
-        }
+        if (mn <= tau) bv_hitq[tid >> 5][atomicAdd(&bv_hitn[tid >> 5], 1u)] = (uint16_t)(stepq | q);
 #else
         if (mn <= tau) {
           uint32_t qq = q;
@@ -553,7 +562,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
           for (int c = 0; c < C; ++c) {
             if ((PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw)) <= tau) {
               const uint32_t j = base + local_of(c);
-              if (j >= c0 && j < c1) bmih_process_hit<W, QS>(&p, t, j, qq);
+              if (j >= c0 && j < c1) bmih_check_code<W, QS>(&p, t, j, qq, code[c]);
             }
           }
         }
@@ -584,9 +593,12 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         __syncwarp();
       }
       // hits of this step: worked off once a warp's worth has gathered, and before the item (its staged queries) is left
-      if (VC_HIT_QUEUE && (hitn >= 32u || (hitn && base + WSTEP >= c1))) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }
+      if (VC_HIT_QUEUE) {
+        const uint32_t hitn = bv_hitn[warp];
+        if (hitn >= 32u || (hitn && base + WSTEP >= c1)) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1, hitn);
+      }
     }
-    if (VC_HIT_QUEUE && hitn) { bmih_drain_hits<W, QS>(&p, t, a0, hitn); hitn = 0; }      // the id cut left the loop early
+    if (VC_HIT_QUEUE && bv_hitn[warp]) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1, bv_hitn[warp]);      // the id cut left the loop early
     if (lane == 0) bv_pairs[warp] += item_pairs;
   }
   if (lane == 0 && p.exec_pairs && bv_pairs[warp]) atomicAdd(p.exec_pairs, bv_pairs[warp]);

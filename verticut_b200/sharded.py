@@ -4,15 +4,18 @@ Replaces the reference's distribution layer for this path - `mpirun -n m` with o
 (src/search_worker.cc:58,99-101,225), MPI_Gatherv of every candidate to rank 0 and MPI_Bcast of the stop
 flag once per radius step (src/mpi_coordinator.cc:26-69, src/search_worker.cc:177,207) - by:
 
-  * rank g owns the contiguous id range [g*N/G, (g+1)*N/G) and ALL m tables over it (shard_range);
-  * queries are replicated; every rank answers them on its shard (exact local top-k; the MIH stop rule
-    is applied per shard, so no collective inside the radius loop);
+  * rank g owns an id-shard - a contiguous range (shard_range) or, what bench.py uses, every G-th id
+    (shard_interleaved) - and ALL m tables over it;
+  * queries are replicated; every rank answers them on its shard (exact local top-k);
   * ONE all-gather of [nq][k] packed words (dist<<32|id) per batch over NVLink, then every rank folds
     the G lists with merge_topk_kernel (shards are id-disjoint, so no de-duplication is needed);
   * inside the MIH search, one small all-reduce per search step sums the per-query distance histograms of
     the shards (vc_index_set_allreduce), so that every GPU filters and stops on the k-th distance of the
     WHOLE database: a shard then does 1/G of the single-GPU work instead of searching to its own, larger,
     local k-th distance.  (The reference exchanges all candidates and a stop flag per radius step.)
+    These per-step exchanges are issued by the library itself - ncclAllReduce on the search stream, from C
+    (vc_nccl_allreduce_hook) - on a communicator created here; VC_NCCL_DIRECT=0 routes them through
+    torch.distributed.all_reduce instead (a Python callback per exchange).
 
 torch.distributed is plumbing here (process group, the all-gather, device buffers); searching and
 merging are the library's CUDA kernels, called through the C ABI with raw device pointers.
@@ -65,16 +68,19 @@ class ShardedSearcher:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs = {}
         self._views = {}
+        self._nccl = None
+        self.exchange = "none"
         if self.world > 1 and global_threshold and hasattr(index, "set_allreduce"):
             index.set_allreduce(self._allreduce_words)
-            if os.environ.get("VC_NCCL_DIRECT") == "1" and hasattr(index, "set_allreduce_nccl"):
+            self.exchange = "torch.distributed.all_reduce (Python callback)"
+            if os.environ.get("VC_NCCL_DIRECT", "1") != "0" and hasattr(index, "set_allreduce_nccl") and dist.get_backend(group) == "nccl":
                 self._nccl_direct()
+                self.exchange = "ncclAllReduce from C on the search stream"
 
     def _nccl_direct(self):
-        """EXPERIMENTAL (VC_NCCL_DIRECT=1; written without a GPU at hand, not measured yet): the library's per-step
-        exchanges call ncclAllReduce themselves (vc_nccl_allreduce_hook) on a communicator of their own instead of coming
-        back to Python for torch.distributed.all_reduce - half a dozen callbacks per search, which at 8 GPUs is a tenth of
-        the batch time.  torch.distributed stays the plumbing: it carries the ncclUniqueId to the other ranks."""
+        """The library's per-step exchanges call ncclAllReduce themselves (vc_nccl_allreduce_hook), on the search stream, on a
+        communicator of their own, instead of coming back to Python for torch.distributed.all_reduce - half a dozen callbacks
+        per search.  torch.distributed stays the plumbing: it carries the ncclUniqueId to the other ranks."""
         import ctypes as C
         t, dist = self.torch, self.dist
         nccl = C.CDLL("libnccl.so.2")                     # by soname: the copy torch has already loaded
@@ -98,8 +104,18 @@ class ShardedSearcher:
         self._nccl = (nccl, comm)                          # keep the library handle and the communicator alive
         self.index.set_allreduce_nccl(C.cast(nccl.ncclAllReduce, C.c_void_p).value, comm.value)
 
+    def close(self):
+        """Releases the library's own NCCL communicator (if any); the index is the caller's."""
+        if self._nccl is not None:
+            nccl, comm = self._nccl
+            self.index.set_allreduce(None)
+            nccl.ncclCommDestroy.argtypes = [type(comm)]
+            nccl.ncclCommDestroy(comm)
+            self._nccl = None
+
     def _allreduce_words(self, ptr, n_words, stream):
-        """Sum n_words int32 words at device address ptr over the ranks (NCCL), ordered after `stream`."""
+        """Sum n_words int32 words at device address ptr over the ranks, ordered after the work already in `stream` (the
+        library's search stream) and before what the library enqueues there next."""
         t = self.torch
         key = (ptr, n_words)
         view = self._views.get(key)
@@ -108,7 +124,11 @@ class ShardedSearcher:
                 __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
             view = t.as_tensor(_Raw(), device=t.device("cuda", self.index.device))
             self._views[key] = view
-        self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+        if view.device.type == "cuda" and int(stream or 0) != t.cuda.current_stream(view.device).cuda_stream:
+            with t.cuda.stream(t.cuda.ExternalStream(int(stream or 0), device=view.device)):
+                self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
 
     def _buffers(self, nq, k, device):
         key = (nq, k, str(device))
@@ -128,6 +148,9 @@ class ShardedSearcher:
         nq = d_queries.shape[0]
         stream = self._stream(d_queries.device)
         if mode == "mih":
+            if self.world > 1 and self.exchange != "none":
+                # the shards' bootstrap samples are summed (bmih_boot_tau_kernel): G shards need 1 / G of the sample each
+                self.index.set_param("mih.boot_sample", max(2048, max(16384, 16 * k) // self.world))
             self.index.search_mih_dev(d_queries.data_ptr(), nq, k, out_keys.data_ptr(), approximate=approximate,
                                       max_radius=max_radius, stream=stream)
         elif mode == "linear":
