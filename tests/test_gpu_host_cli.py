@@ -97,3 +97,44 @@ def test_cli_build_once_search_from_index_file(tmp_path, oracle):
     for q, blk in enumerate(blocks):
         pairs = [(int(a), int(b)) for a, b in re.findall(r"^(\d+) : (\d+)$", blk, flags=re.M)]
         assert pairs == list(zip(oid[q][::-1].tolist(), od[q][::-1].tolist()))
+
+
+def test_reference_positional_command_line(tmp_path, oracle):
+    """distributed-image-search <config> <count> <bits> <substring bits> <k> <server> <read mode> <approximate> <query id> [query file]
+    (src/distributed_image_search.cc:141-156; what run_distributed_search.py:74-79 and the RPC server's popen line start)."""
+    n, nq, k = 20_000, 3, 10
+    codes, queries, cf, qf = _files(tmp_path, oracle, n, 128, nq)
+    idx = str(tmp_path / "tables.vc")
+    _run([os.path.join(BIN, "build-tables"), "-f", cf, "-b", "128", "-n", "8", "-o", idx])
+    exe = os.path.join(BIN, "distributed-image-search")
+    for line in ("index " + idx, "codes " + cf):
+        cfg = tmp_path / "gpu.cnf"
+        cfg.write_text("0\n# tables of this server\n" + line + "\n")
+        # query by id: "id : dist" lines, descending distance (the format image_search_server.cc:94 parses)
+        qid = 17
+        out = _run([exe, str(cfg), str(n), "128", "16", str(k), "gpu", "0", "0", str(qid)])
+        oid, od, _ = oracle.linear_search(codes, codes[qid:qid + 1], k)
+        pairs = [(int(a), int(b)) for a, b in re.findall(r"^(\d+) : (\d+)$", out, flags=re.M)]
+        assert pairs == list(zip(oid[0][::-1].tolist(), od[0][::-1].tolist()))
+        # query file: the averaged statistics line of :87-93
+        out = _run([exe, str(cfg), str(n), "128", "16", str(k), "gpu", "0", "0", "0", qf])
+        m = re.search(r"Averate result : \n0  n_main_reads : 0 , n_sub_reads : (\d+), n_local_reads : (\d+), radius : (\d+), rdma : 0", out)
+        assert m and int(m.group(1)) > 0
+        assert "-------Timings-------" in out
+    # the reference's other servers are not served by this build; too few arguments die as in the reference
+    res = subprocess.run([exe, str(cfg), str(n), "128", "16", str(k), "pilaf", "0", "0", "0"], capture_output=True, text=True)
+    assert res.returncode != 0 and "Unrecognized server type." in res.stderr
+    res = subprocess.run([exe, str(cfg), str(n), "128"], capture_output=True, text=True)
+    assert res.returncode != 0 and "Incorrect number of arguments!" in res.stderr
+
+
+def test_build_tables_writes_generate_bitmap_files(tmp_path, oracle):
+    """build-tables --bitmaps: one raw occupancy bitmap per table, named and laid out as src/generate_bitmap.cc:84-87,119-125."""
+    n = 30_000
+    codes, _, cf, _ = _files(tmp_path, oracle, n, 64, 1)
+    _run([os.path.join(BIN, "build-tables"), "-f", cf, "-b", "64", "-n", "4", "--bitmaps"])
+    oix = oracle.Index(codes, 4)
+    for t in range(4):
+        words = np.fromfile(cf + "_bmp_%d_2b_4k.raw" % (t + 1), dtype=np.uint32)
+        assert words.size == (1 << 16) // 32
+        np.testing.assert_array_equal(words, oix.occupancy_bitmap(t))

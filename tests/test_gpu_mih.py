@@ -73,6 +73,24 @@ def test_occupancy_bitmap_matches_oracle(oracle, bits, m):
     ix.close()
 
 
+def test_occupancy_bitmap_of_sparse_tables(oracle):
+    """s = 32: the 2^32-bit bitmap the device keeps for its sparse tables, exported in the reference's layout (src/bitmap.cc:22-38:
+    bit i of 32-bit word i / 32 - the 512 MiB per table generate_bitmap.cc:99 allocates), against the keys of the codes."""
+    n, bits, m = 50_000, 64, 2
+    codes, ix = _mk(oracle, n, bits, m)
+    keys = codes.view(np.uint32).reshape(n, m)               # little-endian: substring t = 32-bit word t (binaryToInt for s = 32)
+    for t in range(m):
+        words = ix.occupancy_bitmap(t)
+        assert words.size == (1 << 32) // 32
+        set_bits = np.unique(keys[:, t])
+        assert int(np.bitwise_count(words).sum()) == set_bits.size
+        assert ((words[set_bits >> 5] >> (set_bits & 31)) & 1).all()
+        probe = np.array([0, 1, 2 ** 31, 2 ** 32 - 1], dtype=np.uint64)
+        for b in probe:
+            assert bool((words[int(b) >> 5] >> np.uint32(int(b) & 31)) & 1) == bool(np.isin(np.uint32(b), set_bits))
+    ix.close()
+
+
 def _check_exact(oracle, n, bits, m, nq, k, first_id=0):
     codes, ix = _mk(oracle, n, bits, m, first_id=first_id)
     queries = oracle.synth_codes(67890, 0, nq, bits // 8)

@@ -296,28 +296,72 @@ __device__ __noinline__ void bmih_append(const BmihParams* pp, uint32_t qid, uin
   bmih_append_impl<W>(pp, qid, t, d, j, c, qrec, tau_s);
 }
 
-// The verify kernel's per-warp staging areas live at namespace scope so that its rare path finds the warp's slice by
-// itself, from the staged query's index: a pointer argument would have to be kept (in practice: rebuilt from
-// SR_CgaCtaId, seven instructions per record) inside the distance loop, which has no registers to spare.
+// The verify kernel's per-warp state lives at namespace scope, in ONE record per warp, so that (a) the rare paths find the
+// warp's slice by themselves (a pointer argument would have to be kept alive inside the distance loop, which has no registers
+// to spare) and (b) the distance loop addresses all of it - staged queries, hit queue - from a single 32-bit shared-memory
+// address plus constant offsets (ld.shared / atom.shared with explicit addresses below: the generic-pointer form made the
+// compiler carry four addresses through the loop and reload them from local memory for every record).
 constexpr int kBmihQSMax = 12;                                      // BmihCfg<4>::QS
-__shared__ __align__(16) uint32_t bv_qrec[(kBmihThreads / 32) * kBmihQT * kBmihQSMax];
-__shared__ uint32_t bv_qid[kBmihThreads / 32][kBmihQT];
-__shared__ uint16_t bv_hitq[kBmihThreads / 32][kBmihHitQ];          // deferred hits: warp step of the item << 10 | lane << 5 | staged query slot
-__shared__ uint32_t bv_hitn[kBmihThreads / 32];
+struct __align__(16) BvWarp {
+  uint32_t qrec[kBmihQT * kBmihQSMax];   // staged queries: QS words each - the query words, tau, (substituted substring's distance), pad
+  uint32_t qid[kBmihQT];                 // their query indices
+  uint32_t cut[kBmihQT];                 // their k-th ids (id cut of the last step of a search), or ~0
+  uint32_t hitn, pad_[3];                // entries in hitq
+  uint16_t hitq[kBmihHitQ];              // deferred hits: warp step of the item << 10 | lane << 5 | staged query slot
+};
+constexpr uint32_t kBvQid = kBmihQT * kBmihQSMax * 4, kBvCut = kBvQid + kBmihQT * 4, kBvHitN = kBvCut + kBmihQT * 4, kBvHitQ = kBvHitN + 16;
+static_assert(sizeof(BvWarp) == kBvHitQ + kBmihHitQ * 2 && sizeof(BvWarp) % 16 == 0, "BvWarp layout");
+__shared__ BvWarp bv_warp[kBmihThreads / 32];
 __shared__ unsigned long long bv_pairs[kBmihThreads / 32];          // tests executed by the warp (statistics)
 __shared__ const uint64_t* bv_codes[kMaxTables];                    // table payload pointers, fetched once per CTA
 __shared__ const uint32_t* bv_ids[kMaxTables];
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ uint32_t atoms_add_u32(uint32_t a, uint32_t v) {
+  uint32_t o;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+  return o;
+}
+__device__ __forceinline__ void atoms_min_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// one staged query record at shared address a: the query words and its threshold
+template <int W>
+__device__ __forceinline__ QRec<W> lds_qrec(uint32_t a) {
+  QRec<W> r;
+  if constexpr (W == 1) {
+    const uint4 v = lds_u4(a);
+    r.qw[0] = v.x; r.qw[1] = v.y; r.tau = v.z;
+  } else {
+#pragma unroll
+    for (int j = 0; j < W / 2; ++j) {
+      const uint4 v = lds_u4(a + 16 * j);
+      r.qw[4 * j] = v.x; r.qw[4 * j + 1] = v.y; r.qw[4 * j + 2] = v.z; r.qw[4 * j + 3] = v.w;
+    }
+    r.tau = lds_u32(a + 8 * W);
+  }
+  return r;
+}
 
 // One code (position j of table t, bucket order) of a queued hit against staged query qq of this warp: the exact distance
 // against the staged record, and - for the few that really beat the threshold - de-duplication and append.
 template <int W, int QS>
 __device__ __noinline__ void bmih_check_code(const BmihParams* pp, uint32_t t, uint32_t j, uint32_t qq, CodeRegs<W> c) {
-  const uint32_t warp = threadIdx.x >> 5;
-  uint32_t* rec = bv_qrec + warp * (kBmihQT * QS) + qq * QS;
+  BvWarp* w = &bv_warp[threadIdx.x >> 5];
+  uint32_t* rec = w->qrec + qq * QS;
   const uint32_t tau = *(volatile uint32_t*)&rec[2 * W];
   const uint32_t d = hamming_exact<W>(c.w, rec);
   if (d > tau) return;
-  const uint32_t qid = bv_qid[warp][qq];
+  const uint32_t qid = w->qid[qq];
 #if VC_KEY_SUBST
   // d and tau are relative to the staged record: the substring of table t is not part of them (bmih_verify_kernel)
   const uint32_t r_sub = pp->scan_mode ? 0u : rec[2 * W + 1];
@@ -326,19 +370,21 @@ __device__ __noinline__ void bmih_check_code(const BmihParams* pp, uint32_t t, u
   bmih_append_impl<W>(pp, qid, t, d, j, c, rec, tau);
 #endif
 }
-// The warp's n queued hits, 32 at a time (called by all lanes, n warp-uniform).  A hit names a warp step of the item, a lane
-// and a staged query: "one of the C codes that lane held in that step passed the filter for that query".  The draining lane
-// reads those C codes again (they were streamed through this SM a moment ago: L2 hits, same addresses as bmih_verify_kernel's
-// load_step) and checks each exactly - so the distance loop itself never has to find out which code it was.
+// The warp's queued hits, 32 at a time (called by all lanes).  A hit names a warp step of the item, a lane and a staged
+// query: "one of the C codes that lane held in that step passed the filter for that query".  The draining lane reads those C
+// codes again (they were streamed through this SM a moment ago: L2 hits, same addresses as bmih_verify_kernel's load_step)
+// and checks each exactly - so the distance loop itself never has to find out which code it was.
 template <int W, int U4, int QS>
-__device__ __noinline__ void bmih_drain_hits(const BmihParams* pp, uint32_t t, uint32_t a0, uint32_t c0, uint32_t c1, uint32_t n) {
+__device__ __noinline__ void bmih_drain_hits(const BmihParams* pp, uint32_t t, uint32_t a0, uint32_t c0, uint32_t c1) {
   constexpr int C = 2 * U4 / W;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  BvWarp* w = &bv_warp[threadIdx.x >> 5];
+  const uint32_t lane = threadIdx.x & 31;
   const uint4* src = reinterpret_cast<const uint4*>(bv_codes[t] + (size_t)a0 * W);
   const uint32_t u4_last = ((c1 - a0) * W + 1) / 2 - 1;
   __syncwarp();
+  const uint32_t n = min(*(volatile uint32_t*)&w->hitn, (uint32_t)kBmihHitQ);
   for (uint32_t i = lane; i < n; i += 32) {
-    const uint32_t e = bv_hitq[warp][i];
+    const uint32_t e = w->hitq[i];
     const uint32_t step = e >> 10, ln = (e >> 5) & 31u, qq = e & 31u;
     const uint32_t base = a0 + step * (32 * C);
     const uint32_t u4_base = (base - a0) * W / 2;
@@ -365,7 +411,7 @@ __device__ __noinline__ void bmih_drain_hits(const BmihParams* pp, uint32_t t, u
     }
   }
   __syncwarp();
-  if (lane == 0) bv_hitn[warp] = 0;
+  if (lane == 0) w->hitn = 0;
   __syncwarp();
 }
 
@@ -383,15 +429,12 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
   constexpr int C = Cfg::C, QS = Cfg::QS;
   constexpr int NW = kBmihThreads / 32;
   constexpr uint32_t WSTEP = 32 * C;                       // codes per warp step
-  __shared__ uint32_t s_cut_all[NW][kBmihQT];
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
   if (tid < p.m) { bv_codes[tid] = p.tables[tid].codes; bv_ids[tid] = p.tables[tid].ids; }
-  if (tid < NW) { bv_pairs[tid] = 0; bv_hitn[tid] = 0; }
+  if (tid < NW) { bv_pairs[tid] = 0; bv_warp[tid].hitn = 0; }
   __syncthreads();
   static_assert(QS <= kBmihQSMax, "staging area too small");
-  uint32_t* s_qrec = bv_qrec + warp * (kBmihQT * QS);
-  uint32_t* s_qid = bv_qid[warp];
-  uint32_t* s_cut = s_cut_all[warp];
+  const uint32_t wb = smem_u32(&bv_warp[tid >> 5]);       // this warp's state: every hot access below is [wb + constant (+ index)]
   // Codes not found before this step have substring distance >= r + 1 in the tables before t_begin and >= r in the
   // others: distance >= lb.  A query whose k-th best is already AT that distance can only improve by ties with a
   // smaller id - and a bucket is in ascending id order, so that query is done with a bucket at the first id >= its
@@ -427,7 +470,7 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
 #pragma unroll
       for (int u = 0; u < U4; ++u) {
         // lanes past the end of the item re-read its last 16 bytes (no predicate, no zero fill): what they find is
-        // dropped by the range test in front of the hit queue
+        // dropped by the range test of the hit path
         uint4 v;
         if constexpr (W == 1) {
           const uint32_t idx = min(u4_base + u * 32 + lane, u4_last);
@@ -445,10 +488,6 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         }
       }
     };
-    auto local_of = [&](int c) -> uint32_t {
-      if constexpr (W == 1) return 2 * ((c / 2) * 32 + lane) + (c & 1);
-      else return c * 32 + lane;
-    };
     load_step(a0);                                     // the first codes travel while the queries are staged
     {
       // ... and so do the next kPfDist - 1 steps, into L2 (two lines per lane and step)
@@ -459,43 +498,47 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       }
     }
     __syncwarp();                                      // previous item's readers are done with the warp's slice
-    for (uint32_t e = lane; e < qn * QS; e += 32) {
-      const uint32_t i = e / QS, w = e % QS;
-      const uint32_t qid = p.qlist[qbeg + i];
-      if (w == 0) s_qid[i] = qid;
-      s_qrec[e] = w < 2 * W ? p.queries[(size_t)qid * 2 * W + w] : (w == 2 * W ? __ldcg(&p.gtau[qid]) : 0u);
-    }
-#if VC_KEY_SUBST
-    // Every code of the item has the bucket's key as its substring t, so that substring adds the same r_own = popc(query
-    // substring ^ key) to every distance.  With the key written into the staged query the XOR is zero there: the one-POPC lower
-    // bound no longer loses those 16 bits to the OR with their partner substring, and is tested against tau - r_own (a sharper
-    // filter at no cost per test: 128-bit codes at radius 4, tau = 36: 0.07 % instead of 0.4 % of the codes pass it).  The hit
-    // path adds r_own back and takes the query's own words for the first-discoverer test; a threshold below r_own is clamped
-    // to 0, which can only let codes through that the append path then handles with their true distance.
-    static_assert(QS >= 2 * W + 2, "no spare word in the staged record");
-    if (!p.scan_mode) {
-      __syncwarp();
-      if (lane < qn) {
-        uint32_t* rec = s_qrec + lane * QS;
-        const uint32_t key = substring<W>(reinterpret_cast<const uint32_t*>(bv_codes[t] + (size_t)c0 * W), t, p.sbits);
-        const uint32_t off = t * p.sbits, wi = off >> 5, sh = off & 31;
-        const uint32_t mask = (p.sbits == 32 ? 0xFFFFFFFFu : ((1u << p.sbits) - 1u)) << sh;
-        const uint32_t qw = rec[wi];
-        const uint32_t r_own = __popc((qw ^ (key << sh)) & mask);
-        rec[wi] = (qw & ~mask) | (key << sh);
-        const uint32_t tau0 = rec[2 * W];
-        rec[2 * W] = tau0 >= r_own ? tau0 - r_own : 0u;
-        rec[2 * W + 1] = r_own;
+    {
+      BvWarp* w = &bv_warp[tid >> 5];
+      for (uint32_t e = lane; e < qn * QS; e += 32) {
+        const uint32_t i = e / QS, x = e % QS;
+        const uint32_t qid = p.qlist[qbeg + i];
+        if (x == 0) w->qid[i] = qid;
+        w->qrec[e] = x < 2 * W ? p.queries[(size_t)qid * 2 * W + x] : (x == 2 * W ? __ldcg(&p.gtau[qid]) : 0u);
       }
-    }
+#if VC_KEY_SUBST
+      // Every code of the item has the bucket's key as its substring t, so that substring adds the same r_own = popc(query
+      // substring ^ key) to every distance.  With the key written into the staged query the XOR is zero there: the one-POPC
+      // lower bound no longer loses those 16 bits to the OR with their partner substring, and is tested against tau - r_own (a
+      // sharper filter at no cost per test: 128-bit codes at radius 4, tau = 37: a fifth instead of two thirds of the
+      // warp-records contain a code that passes it).  The hit path adds r_own back and takes the query's own words for the
+      // first-discoverer test; a threshold below r_own is clamped to 0, which can only let codes through that the append path
+      // then handles with their true distance.
+      static_assert(QS >= 2 * W + 2, "no spare word in the staged record");
+      if (!p.scan_mode) {
+        __syncwarp();
+        if (lane < qn) {
+          uint32_t* rec = w->qrec + lane * QS;
+          const uint32_t key = substring<W>(reinterpret_cast<const uint32_t*>(bv_codes[t] + (size_t)c0 * W), t, p.sbits);
+          const uint32_t off = t * p.sbits, wi = off >> 5, sh = off & 31;
+          const uint32_t mask = (p.sbits == 32 ? 0xFFFFFFFFu : ((1u << p.sbits) - 1u)) << sh;
+          const uint32_t qw = rec[wi];
+          const uint32_t r_own = __popc((qw ^ (key << sh)) & mask);
+          rec[wi] = (qw & ~mask) | (key << sh);
+          const uint32_t tau0 = rec[2 * W];
+          rec[2 * W] = tau0 >= r_own ? tau0 - r_own : 0u;
+          rec[2 * W + 1] = r_own;
+        }
+      }
 #endif
-    uint32_t my_cut = 0xFFFFFFFFu;
-    if (!p.scan_mode && lane < qn) {
-      const uint64_t tk = __ldcg(&p.gtaukey[p.qlist[qbeg + lane]]);
-      if ((uint32_t)(tk >> 32) == lb) my_cut = (uint32_t)tk;
+      uint32_t my_cut = 0xFFFFFFFFu;
+      if (!p.scan_mode && lane < qn) {
+        const uint64_t tk = __ldcg(&p.gtaukey[p.qlist[qbeg + lane]]);
+        if ((uint32_t)(tk >> 32) == lb) my_cut = (uint32_t)tk;
+      }
+      w->cut[lane] = my_cut;
     }
-    s_cut[lane] = my_cut;
-    const bool use_cut = __any_sync(0xffffffffu, my_cut != 0xFFFFFFFFu);
+    const bool use_cut = __any_sync(0xffffffffu, lds_u32(wb + kBvCut + 4 * lane) != 0xFFFFFFFFu);
     uint32_t qlive = qn;                               // staged queries still interested in the rest of the item
     uint32_t item_pairs = use_cut ? 0u : (c1 - c0) * qn;       // tests of this item (no query leaves early: counted once; < 2^32: cpi * 32)
     __syncwarp();
@@ -503,26 +546,28 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       if (use_cut) {
         // queries whose k-th id lies at or before the first id of this step are done with the bucket: the staged list
         // is compacted (each query leaves once), the distance loop below stays dense
+        BvWarp* w = &bv_warp[tid >> 5];
         const uint32_t fid = __ldg(&bv_ids[t][max(base, c0)]);
-        const bool keep = lane < qlive && s_cut[lane] > fid;
+        const bool keep = lane < qlive && w->cut[lane] > fid;
         const uint32_t alive = __ballot_sync(0xffffffffu, keep);
         if (!alive) break;
         if (alive != (qlive >= 32 ? 0xFFFFFFFFu : ((1u << qlive) - 1u))) {
-          if (VC_HIT_QUEUE && bv_hitn[warp]) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1, bv_hitn[warp]);     // queued hits name staged slots: before they move
+          if (VC_HIT_QUEUE && *(volatile uint32_t*)&w->hitn) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1);     // queued hits name staged slots: before they move
           uint32_t rec[QS];
 #pragma unroll
-          for (int i = 0; i < QS; ++i) rec[i] = keep ? s_qrec[lane * QS + i] : 0u;
-          const uint32_t mq = keep ? s_qid[lane] : 0u, mc = keep ? s_cut[lane] : 0u;
+          for (int i = 0; i < QS; ++i) rec[i] = keep ? w->qrec[lane * QS + i] : 0u;
+          const uint32_t mq = keep ? w->qid[lane] : 0u, mc = keep ? w->cut[lane] : 0u;
           __syncwarp();
           if (keep) {
             const uint32_t pos = __popc(alive & ((1u << lane) - 1u));
 #pragma unroll
-            for (int i = 0; i < QS; ++i) s_qrec[pos * QS + i] = rec[i];
-            s_qid[pos] = mq; s_cut[pos] = mc;
+            for (int i = 0; i < QS; ++i) w->qrec[pos * QS + i] = rec[i];
+            w->qid[pos] = mq; w->cut[pos] = mc;
           }
           qlive = __popc(alive);
           __syncwarp();
         }
+        item_pairs += (min(c1, base + WSTEP) - max(base, c0)) * qlive;
       }
       if (base != a0) load_step(base);
       if constexpr (kPfDist > 0) {
@@ -530,16 +575,15 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         const uint32_t ahead = (base - a0 + kPfDist * WSTEP) * W / 2;
         if (lane < 16 && ahead + lane * 8 < u4_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + ahead + lane * 8));
       }
-      if (use_cut) item_pairs += (min(c1, base + WSTEP) - max(base, c0)) * qlive;
       // keep the staged thresholds current: other warps (and, sharded, other GPUs) lower them all the time, and at
       // small radii - where the candidates are near neighbours by construction - a stale tau sends a large share
       // of the codes down the slow path.  The load is issued here and consumed after this step's math.
       uint32_t fresh_tau = kInfDist;
       const bool refresh = VC_TAU_EVERY == 1 || (((base - a0) / WSTEP) % VC_TAU_EVERY) == VC_TAU_EVERY - 1;
-      if (refresh && lane < qlive) fresh_tau = __ldcg(&p.gtau[s_qid[lane]]);
-      // one staged query against this thread's C codes: the minimum of the (lower-bound) distances decides; the rare
-      // hit recomputes per code
-      const uint32_t stepq = (((base - a0) / WSTEP) << 10) | (lane << 5);      // this lane's hit-queue word, without the query slot
+      if (refresh && lane < qlive) fresh_tau = __ldcg(&p.gtau[lds_u32(wb + kBvQid + 4 * lane)]);
+      // one staged query (record at shared address qa) against this thread's C codes: the minimum of the (lower-bound)
+      // distances decides; a lane whose minimum passes queues (step, lane, query slot) and moves on
+      const uint32_t stepq = (((base - a0) / WSTEP) << 10) | (lane << 5);
       auto test_query = [&](const QRec<W>& cur, uint32_t q) {
         const uint32_t tau = cur.tau;
         uint32_t mn;
@@ -553,55 +597,63 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
           for (int c = 0; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
         }
 #if VC_HIT_QUEUE
-        if (mn <= tau) bv_hitq[tid >> 5][atomicAdd(&bv_hitn[tid >> 5], 1u)] = (uint16_t)(stepq | q);
+        if (mn <= tau) {
+          // the warp's queue is found from the thread index INSIDE the branch (the empty asm keeps the compiler from hoisting
+          // the address out of the loop, where it would cost a register - or a reload from local memory - per record)
+          uint32_t tw = threadIdx.x >> 5;
+          asm volatile("" : "+r"(tw));
+          BvWarp* w = &bv_warp[tw];
+          w->hitq[atomicAdd(&w->hitn, 1u)] = (uint16_t)(stepq | q);
+        }
 #else
         if (mn <= tau) {
-          uint32_t qq = q;
-          asm volatile("" : "+r"(qq));        // keeps the address arithmetic of this rare path out of the loop body
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             if ((PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw)) <= tau) {
-              const uint32_t j = base + local_of(c);
-              if (j >= c0 && j < c1) bmih_check_code<W, QS>(&p, t, j, qq, code[c]);
+              const uint32_t j = base + (W == 1 ? 2 * ((c / 2) * 32 + lane) + (c & 1) : c * 32 + lane);
+              if (j >= c0 && j < c1) bmih_check_code<W, QS>(&p, t, j, q, code[c]);
             }
           }
         }
 #endif
       };
       // two records in flight, ping-pong: the next record's LDS overlaps this record's math, without register moves
-      QRec<W> ra = load_qrec<W, QS>(s_qrec, 0), rb;
+      {
+        uint32_t qa = wb;
+        QRec<W> ra = lds_qrec<W>(qa), rb;
 #pragma unroll 1
-      for (uint32_t q = 0; q < qlive; q += 2) {
-        if (q + 1 < qlive) rb = load_qrec<W, QS>(s_qrec, q + 1);
-        test_query(ra, q);
-        if (q + 1 < qlive) {
-          if (q + 2 < qlive) ra = load_qrec<W, QS>(s_qrec, q + 2);
-          test_query(rb, q + 1);
+        for (uint32_t q = 0; q < qlive; q += 2, qa += 2 * (4 * QS)) {
+          if (q + 1 < qlive) rb = lds_qrec<W>(qa + 4 * QS);
+          test_query(ra, q);
+          if (q + 1 < qlive) {
+            if (q + 2 < qlive) ra = lds_qrec<W>(qa + 2 * (4 * QS));
+            test_query(rb, q + 1);
+          }
         }
       }
       __syncwarp();
       if (refresh) {
-#if VC_KEY_SUBST
         if (lane < qlive) {
-          const uint32_t r_own = s_qrec[lane * QS + 2 * W + 1];
+#if VC_KEY_SUBST
+          const uint32_t r_own = lds_u32(wb + lane * (4 * QS) + 4 * (2 * W + 1));
           const uint32_t ft = fresh_tau >= r_own ? fresh_tau - r_own : 0u;
-          if (ft < s_qrec[lane * QS + 2 * W]) atomicMin(&s_qrec[lane * QS + 2 * W], ft);
-        }
 #else
-        if (lane < qlive && fresh_tau < s_qrec[lane * QS + 2 * W]) atomicMin(&s_qrec[lane * QS + 2 * W], fresh_tau);
+          const uint32_t ft = fresh_tau;
 #endif
+          if (ft < lds_u32(wb + lane * (4 * QS) + 8 * W)) atoms_min_u32(wb + lane * (4 * QS) + 8 * W, ft);
+        }
         __syncwarp();
       }
       // hits of this step: worked off once a warp's worth has gathered, and before the item (its staged queries) is left
       if (VC_HIT_QUEUE) {
-        const uint32_t hitn = bv_hitn[warp];
-        if (hitn >= 32u || (hitn && base + WSTEP >= c1)) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1, hitn);
+        const uint32_t hitn = lds_u32(wb + kBvHitN);
+        if (hitn >= 32u || (hitn && base + WSTEP >= c1)) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1);
       }
     }
-    if (VC_HIT_QUEUE && bv_hitn[warp]) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1, bv_hitn[warp]);      // the id cut left the loop early
-    if (lane == 0) bv_pairs[warp] += item_pairs;
+    if (VC_HIT_QUEUE && lds_u32(wb + kBvHitN)) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1);      // the id cut left the loop early
+    if (lane == 0) bv_pairs[tid >> 5] += item_pairs;
   }
-  if (lane == 0 && p.exec_pairs && bv_pairs[warp]) atomicAdd(p.exec_pairs, bv_pairs[warp]);
+  if (lane == 0 && p.exec_pairs && bv_pairs[tid >> 5]) atomicAdd(p.exec_pairs, bv_pairs[tid >> 5]);
 }
 
 // ---- 4. settle: per query after a step --------------------------------------------------------------------

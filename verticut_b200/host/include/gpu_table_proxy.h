@@ -50,12 +50,16 @@ class GpuTableProxy : public BaseProxy<google::protobuf::Message, google::protob
   int code_bytes() const { return bits_ / 8; }
   int n_tables() const { return tables_; }
   const char* last_error() const { return vc_last_error(); }
+  // what the config file of init() said about the origin of the tables ("index <file>" / "codes <file>" lines); empty if nothing
+  const std::string& config_index_path() const { return index_path_; }
+  const std::string& config_codes_path() const { return codes_path_; }
 
  private:
   GpuTableProxy(const GpuTableProxy&);
   int bits_, tables_, device_;
   uint32_t first_id_;
   vc_index* ix_;
+  std::string index_path_, codes_path_;
   bool dirty_;                                             // codes added since the last build
   std::map<uint32_t, std::string> staged_codes_;           // id -> code, from put(); drained by finalize()
   std::unordered_map<uint64_t, Image_List> staged_lists_;  // (table << 32 | index) -> value, LOADING state only

@@ -1,9 +1,12 @@
 #include "gpu_table_proxy.h"
 
+#include <ctype.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <fstream>
+#include <sstream>
 #include <vector>
 
 GpuTableProxy::GpuTableProxy(int binary_bits, int n_tables, uint32_t first_id)
@@ -13,11 +16,27 @@ GpuTableProxy::~GpuTableProxy() { close(); }
 
 int GpuTableProxy::init(const char* filename) {
   device_ = 0;
+  index_path_.clear(); codes_path_.clear();
   if (filename) {
     std::ifstream fin(filename);
     if (!fin.is_open()) return -1;             // same failure mode as the reference's proxies
-    int dev;
-    if (fin >> dev) device_ = dev;
+    // "server list" of the GPU backend: the first bare number is the CUDA device ordinal; optional lines
+    // "index <file>" / "codes <file>" say where this server's tables come from (the reference's servers hold theirs
+    // already; tools started with the reference's positional arguments have no other way to name them)
+    std::string line;
+    bool have_dev = false;
+    while (std::getline(fin, line)) {
+      std::istringstream ls(line);
+      std::string tok;
+      if (!(ls >> tok) || tok[0] == '#') continue;
+      if (tok == "index" || tok == "codes") {
+        std::string path;
+        if (ls >> path) (tok == "index" ? index_path_ : codes_path_) = path;
+      } else if (!have_dev && (isdigit((unsigned char)tok[0]))) {
+        device_ = atoi(tok.c_str());
+        have_dev = true;
+      }
+    }
   }
   if (ix_) { vc_index_destroy(ix_); ix_ = 0; }
   if (vc_index_create(device_, (uint32_t)bits_, (uint32_t)tables_, first_id_, &ix_) != VC_OK) {
