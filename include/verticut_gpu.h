@@ -171,6 +171,29 @@ int vc_index_set_allreduce(vc_index* ix, vc_allreduce_fn fn, void* user);
 typedef struct vc_nccl_hook { void* nccl_allreduce; void* comm; } vc_nccl_hook;
 int vc_nccl_allreduce_hook(void* user, uint32_t* d_words, uint64_t n_words, void* stream);
 
+/* Peer exchange: the id-sharded search over the GPUs of ONE box without NCCL on the data path - every shard stores its
+ * per-step histograms and its local top-k rows straight into the other GPUs' memory over NVLink / NVSwitch (CUDA IPC windows,
+ * flags with system-scope release / acquire; verticut_b200/csrc/xchg.cuh).  Replaces src/mpi_coordinator.cc:26-69 and the
+ * per-radius exchange of src/search_worker.cc:177,207 like the hook above does, and the all-gather + merge of the results too.
+ *   vc_xchg_create      allocates this rank's window (two sets of `world` slots of slot_bytes each - the largest payload one
+ *                       rank contributes to one exchange: max(nq * k * 8, nq * (64 * W + 32) * 4, nq * 257 * 4) for the batches to
+ *                       come; larger payloads fall back to the hook) and returns its CUDA IPC handle (VC_XCHG_HANDLE_BYTES
+ *                       bytes) for the other processes; out_handle may be NULL when all shards live in one process
+ *   vc_xchg_open        opens the windows of all ranks from their handles (world x VC_XCHG_HANDLE_BYTES bytes, rank order; the
+ *                       entry of this rank is ignored); vc_xchg_open_ptrs does the same from device pointers (one process)
+ *   vc_search_sharded_dev   local search (mih = 1: vc_search_mih_dev, 0: vc_search_linear_dev) + exchange of the local
+ *                       top-k + merge kernel: d_out_keys [nq][k] is the answer over the whole database, identical on every
+ *                       rank.  All ranks must call it with the same arguments, in the same order, on streams that make progress
+ *                       concurrently (a rank waits for its peers inside the call; a peer that never arrives ends the wait
+ *                       with VC_ERR_STATE after 20 s).  Knob "xchg" = 0 turns the peer path off (hook / NCCL only). */
+#define VC_XCHG_HANDLE_BYTES 64
+int vc_xchg_create(vc_index* ix, uint32_t rank, uint32_t world, uint64_t slot_bytes, void* out_handle);
+int vc_xchg_local_window(vc_index* ix, void** window);
+int vc_xchg_open(vc_index* ix, const void* handles);
+int vc_xchg_open_ptrs(vc_index* ix, void* const* peer_windows);
+int vc_search_sharded_dev(vc_index* ix, int mih, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                          uint64_t* d_out_keys, void* stream);
+
 /* Knobs and counters (integers).  Unknown names return VC_ERR_ARG.
  *   "id_stride"   id of the j-th code added = first_id + j * id_stride (default 1; G for one of G interleaved shards;
  *                 must be set before codes are added; stored by vc_index_save)

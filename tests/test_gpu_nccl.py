@@ -1,6 +1,7 @@
-"""The id-sharded search over REAL NCCL: one process per GPU, the per-step all-reduces of the distance / id histograms inside the
-batched MIH search, the all-gather of the local top-k and the merge kernel - merged answers vs the CPU oracle, bit-exact, on every
-rank.  This is the path that replaces src/mpi_coordinator.cc:34-69 (gather_vectors / bcast) and the per-radius exchange of
+"""The id-sharded search across REAL GPUs, one process per GPU, in its three forms: peer-memory exchange over NVLink (the search
+kernels store their histogram rows and top-k rows into the other GPU's window, verticut_b200/csrc/xchg.cuh - the default),
+ncclAllReduce issued from C + NCCL all-gather, and torch.distributed.all_reduce through the Python callback - merged answers vs
+the CPU oracle, bit-exact, on every rank.  This is the path that replaces src/mpi_coordinator.cc:34-69 (gather_vectors / bcast) and the per-radius exchange of
 src/search_worker.cc:177,207.  Needs >= 2 visible GPUs (gpurun --gpus 2); skipped on a one-GPU box, where
 tests/test_gpu_sharded.py covers the same kernels with the exchange emulated between two host threads."""
 import os
@@ -35,6 +36,7 @@ def _worker(rank, world, port, cfg, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["VC_NCCL_DIRECT"] = "1" if cfg["direct"] else "0"
+    os.environ["VC_XCHG"] = "1" if cfg["xchg"] else "0"
     import torch
     import torch.distributed as dist
     from verticut_b200 import capi
@@ -54,7 +56,9 @@ def _worker(rank, world, port, cfg, ret):
     ix.build()
     ix.set_param("mih.batched", 1)
     s = ShardedSearcher(ix)
-    assert ("ncclAllReduce" in s.exchange) == bool(cfg["direct"]), s.exchange
+    assert s.peer_windows == bool(cfg["xchg"]), s.exchange
+    if not cfg["xchg"]:
+        assert ("ncclAllReduce" in s.exchange) == bool(cfg["direct"]), s.exchange
     q = torch.from_numpy(cfg["queries"]).to(dev)
     out = {}
     for mode in ("mih", "linear"):
@@ -63,6 +67,7 @@ def _worker(rank, world, port, cfg, ret):
             torch.cuda.synchronize()
         out[mode] = res.cpu().numpy().view(np.uint64).copy()
     out["batched"] = ix.get_param("mih.last_batched")
+    out["xchg_last"] = ix.get_param("xchg.last")
     out["levels"] = ix.get_param("mih.last_levels")
     ret[rank] = out
     dist.barrier()
@@ -72,16 +77,19 @@ def _worker(rank, world, port, cfg, ret):
 
 
 CASES = [
-    dict(bits=64, m=4, n=3_000_001, nq=96, k=100, r=-1, interleaved=True, direct=True),
-    dict(bits=64, m=4, n=3_000_001, nq=96, k=100, r=-1, interleaved=True, direct=False),
-    dict(bits=128, m=8, n=1_500_000, nq=40, k=100, r=-1, interleaved=True, direct=True),
-    dict(bits=64, m=4, n=2_000_000, nq=33, k=10, r=-1, interleaved=False, direct=True),
-    dict(bits=256, m=16, n=600_000, nq=16, k=1000, r=2, interleaved=True, direct=True),
+    dict(bits=64, m=4, n=3_000_001, nq=96, k=100, r=-1, interleaved=True, direct=True, xchg=True),
+    dict(bits=64, m=4, n=3_000_001, nq=96, k=100, r=-1, interleaved=True, direct=True, xchg=False),
+    dict(bits=64, m=4, n=3_000_001, nq=96, k=100, r=-1, interleaved=True, direct=False, xchg=False),
+    dict(bits=128, m=8, n=1_500_000, nq=40, k=100, r=-1, interleaved=True, direct=True, xchg=True),
+    dict(bits=64, m=4, n=2_000_000, nq=33, k=11, r=-1, interleaved=False, direct=True, xchg=True),
+    dict(bits=256, m=16, n=600_000, nq=16, k=1000, r=2, interleaved=True, direct=True, xchg=True),
+    dict(bits=256, m=16, n=600_000, nq=16, k=1000, r=2, interleaved=True, direct=True, xchg=False),
 ]
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("cfg", CASES, ids=lambda c: "%dbit-m%d-k%d-r%d-%s-%s" % (c["bits"], c["m"], c["k"], c["r"], "il" if c["interleaved"] else "range", "direct" if c["direct"] else "torch"))
+@pytest.mark.parametrize("cfg", CASES, ids=lambda c: "%dbit-m%d-k%d-r%d-%s-%s" % (c["bits"], c["m"], c["k"], c["r"], "il" if c["interleaved"] else "range",
+                                                                    "peer" if c["xchg"] else ("nccl" if c["direct"] else "torch")))
 def test_two_ranks_over_nccl_equal_the_oracle(oracle, cfg):
     import torch.multiprocessing as mp
     world = 2
@@ -100,5 +108,6 @@ def test_two_ranks_over_nccl_equal_the_oracle(oracle, cfg):
                                                                  max_radius=cfg["r"], n_procs=4)
     for r in range(world):
         assert ret[r]["batched"] == 1
+        assert (ret[r]["xchg_last"] > 0) == bool(cfg["xchg"])
         np.testing.assert_array_equal(ret[r]["linear"], want_scan)      # P1 / P5: independent of the sharding, same on every rank
         np.testing.assert_array_equal(ret[r]["mih"], want_mih)          # P2

@@ -196,3 +196,62 @@ def test_two_shards_with_live_exchange(oracle, table_steps):
     oid, od, oc = oracle.linear_search(codes, queries, k)
     np.testing.assert_array_equal(mi, oid)
     np.testing.assert_array_equal(md, od)
+
+
+def test_two_shards_over_peer_windows(oracle):
+    """The peer-memory exchange (verticut_b200/csrc/xchg.cuh) between two shards on ONE GPU: each shard's window is opened by
+    the other through its device pointer (vc_xchg_open_ptrs), two host threads search at the same time on two streams; the settle
+    kernel's histogram rows and the finish kernel's top-k rows go through the windows, vc_search_sharded_dev returns the merged
+    answer on both "ranks".  Merged result == oracle, exactly, for the MIH search, the linear scan and a fixed-radius search."""
+    import threading
+    import torch
+    n, nq, k, G = 1_200_000, 48, 100, 2
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    dq = torch.from_numpy(queries).cuda()
+    ixs = []
+    for g in range(G):
+        first, stride, cnt = shard_interleaved(n, G, g)
+        ix = capi.Index(64, 4, first_id=first)
+        ix.set_param("id_stride", stride)
+        ix.add_synthetic(cnt, 12345)
+        ix.build()
+        ix.set_param("mih.batched", 1)
+        ix.search_mih(queries, k)                       # every scratch buffer of the unsharded path exists before the threads start
+        ix.search_linear(queries, k)
+        ixs.append(ix)
+    for g in range(G):
+        ixs[g].xchg_create(g, G, 4 << 20)
+    wins = [ix.xchg_local_window() for ix in ixs]
+    for g in range(G):
+        ixs[g].xchg_open_ptrs(wins)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(G)]
+    outs = [[torch.empty((nq, k), dtype=torch.int64, device="cuda") for _ in range(3)] for _ in range(G)]
+    errors = []
+
+    def run(g):
+        try:
+            with torch.cuda.stream(streams[g]):
+                s = streams[g].cuda_stream
+                ixs[g].search_sharded_dev(True, dq.data_ptr(), nq, k, outs[g][0].data_ptr(), stream=s)
+                assert ixs[g].get_param("xchg.last") >= 3       # bootstrap + one per step + the result rows
+                ixs[g].search_sharded_dev(False, dq.data_ptr(), nq, k, outs[g][1].data_ptr(), stream=s)
+                ixs[g].search_sharded_dev(True, dq.data_ptr(), nq, k, outs[g][2].data_ptr(), max_radius=1, stream=s)
+                streams[g].synchronize()
+        except Exception as ex:
+            errors.append(ex)
+
+    threads = [threading.Thread(target=run, args=(g,)) for g in range(G)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    want = oracle.scan_synth(12345, 0, 1, n, 8, queries, k, n_procs=4)
+    want_r1 = oracle.scan_synth(12345, 0, 1, n, 8, queries, k, m=4, max_radius=1, n_procs=4)
+    for g in range(G):
+        np.testing.assert_array_equal(outs[g][0].cpu().numpy().view(np.uint64), want)
+        np.testing.assert_array_equal(outs[g][1].cpu().numpy().view(np.uint64), want)
+        np.testing.assert_array_equal(outs[g][2].cpu().numpy().view(np.uint64), want_r1)
+        ixs[g].close()

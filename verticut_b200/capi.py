@@ -26,8 +26,9 @@ EXPORTS = [
     "vc_bucket_get", "vc_code_get", "vc_occupancy_bitmap_get", "vc_search_linear", "vc_search_mih",
     "vc_search_linear_dev", "vc_search_mih_dev", "vc_merge_topk_dev", "vc_merge_topk",
     "vc_index_set_param", "vc_index_get_param", "vc_index_set_allreduce", "vc_index_save", "vc_index_load",
-    "vc_nccl_allreduce_hook",
+    "vc_nccl_allreduce_hook", "vc_xchg_create", "vc_xchg_local_window", "vc_xchg_open", "vc_xchg_open_ptrs", "vc_search_sharded_dev",
 ]
+XCHG_HANDLE_BYTES = 64
 
 
 class VerticutError(RuntimeError):
@@ -95,6 +96,11 @@ def lib():
     L.vc_merge_topk.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.vc_index_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
     L.vc_nccl_allreduce_hook.argtypes = [vp, vp, C.c_uint64, vp]
+    L.vc_xchg_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint64, vp]
+    L.vc_xchg_local_window.argtypes = [vp, C.POINTER(vp)]
+    L.vc_xchg_open.argtypes = [vp, vp]
+    L.vc_xchg_open_ptrs.argtypes = [vp, C.POINTER(vp)]
+    L.vc_search_sharded_dev.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, vp]
     L.vc_index_set_param.argtypes = [vp, C.c_char_p, C.c_int64]
     L.vc_index_get_param.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
     _lib = L
@@ -200,6 +206,32 @@ class Index:
         self._allreduce_cb = None
         fn = C.cast(lib().vc_nccl_allreduce_hook, ALLREDUCE_FN)
         check(lib().vc_index_set_allreduce(self.h, fn, C.cast(C.pointer(self._nccl_hook), C.c_void_p)))
+
+    # ---- peer exchange over NVLink peer memory (vc_xchg_*) ------------------------------------------------
+    def xchg_create(self, rank, world, slot_bytes):
+        """Allocates this rank's exchange window; returns its CUDA IPC handle (bytes) for the other processes."""
+        h = (C.c_ubyte * XCHG_HANDLE_BYTES)()
+        check(lib().vc_xchg_create(self.h, rank, world, slot_bytes, C.cast(h, C.c_void_p)))
+        return bytes(h)
+
+    def xchg_local_window(self):
+        p = C.c_void_p()
+        check(lib().vc_xchg_local_window(self.h, C.byref(p)))
+        return p.value
+
+    def xchg_open(self, handles):
+        """handles: the IPC handles of all ranks back to back (world x 64 bytes, rank order)."""
+        buf = (C.c_ubyte * len(handles)).from_buffer_copy(handles)
+        check(lib().vc_xchg_open(self.h, C.cast(buf, C.c_void_p)))
+
+    def xchg_open_ptrs(self, windows):
+        """windows: device pointers of all ranks' windows (all shards in one process)."""
+        arr = (C.c_void_p * len(windows))(*[C.c_void_p(w) for w in windows])
+        check(lib().vc_xchg_open_ptrs(self.h, arr))
+
+    def search_sharded_dev(self, mih, d_queries, nq, k, d_out_keys, approximate=False, max_radius=-1, stream=0):
+        check(lib().vc_search_sharded_dev(self.h, int(bool(mih)), C.c_void_p(d_queries), nq, k, int(approximate), int(max_radius),
+                                          C.c_void_p(d_out_keys), C.c_void_p(stream)))
 
     def set_param(self, name, value):
         check(lib().vc_index_set_param(self.h, name.encode(), int(value)))

@@ -17,6 +17,7 @@
 #include "scan.cuh"
 #include "bmih.cuh"
 #include "tcverify.cuh"
+#include "xchg.cuh"
 
 using namespace vc;
 
@@ -135,6 +136,22 @@ struct vc_index {
   int64_t tc_units = 0, tc_flagged = 0, tc_hits = 0;     // statistics of the tensor-core launches of the last search
   vc_allreduce_fn allreduce_fn = nullptr;
   void* allreduce_user = nullptr;
+  // peer exchange over NVLink peer memory (xchg.cuh): window of this rank, the peers' windows, running exchange number
+  uint32_t x_rank = 0, x_world = 0;
+  uint64_t x_slot_bytes = 0;
+  unsigned char* x_window = nullptr;
+  unsigned char* x_peer[kXchgMaxWorld] = {nullptr};
+  bool x_ipc[kXchgMaxWorld] = {false};
+  bool x_open = false;
+  uint32_t x_seq = 0, x_done_total = 0;
+  uint32_t* x_ctr = nullptr;      // device: [0] CTAs that finished a push (running total), [1] a wait timed out
+  DevBuf x_local;                 // local top-k of a sharded search call
+  bool x_fuse_finish = false;     // the next batched search pushes its result rows from bmih_finish_kernel itself ...
+  bool x_pushed = false;          // ... and says here whether it did
+  XchgDev x_finish;               // ... into this exchange
+  int64_t x_enabled = 1;          // knob "xchg": 0 = keep the all-reduce hook / NCCL for everything
+  int64_t last_xchg = 0;          // exchanges of the last search that went over peer memory
+  bool sharded() const { return allreduce_fn != nullptr || x_open; }
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
   int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0, last_mih_redo = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
@@ -237,6 +254,10 @@ void vc_index_destroy(vc_index* ix) {
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
   for (PinBuf* b : pb) b->release();
+  for (uint32_t g2 = 0; g2 < ix->x_world; ++g2) if (ix->x_ipc[g2] && ix->x_peer[g2]) cudaIpcCloseMemHandle(ix->x_peer[g2]);
+  if (ix->x_window) cudaFree(ix->x_window);
+  if (ix->x_ctr) cudaFree(ix->x_ctr);
+  ix->x_local.release();
   delete ix;
 }
 
@@ -601,7 +622,8 @@ static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 
 
 // lists [n_lists][nq][k] -> out [nq][k]; uses `scratch` (>= ceil(n_lists/fanin) * nq * k keys) for the tree levels
 static int merge_lists(int64_t* launches, const uint64_t* d_lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t fanin,
-                       uint64_t* d_scratch_a, uint64_t* d_scratch_b, uint64_t* d_out, cudaStream_t st) {
+                       uint64_t* d_scratch_a, uint64_t* d_scratch_b, uint64_t* d_out, cudaStream_t st, uint64_t list_stride = 0) {
+  if (!list_stride) list_stride = (uint64_t)nq * k;
   const uint32_t BUF = pow2_at_least(k + kMergeThreads);     // <= 4096 entries = 32 KB: no opt-in needed
   const size_t smem = (size_t)BUF * 8;
   const uint64_t* in = d_lists;
@@ -611,11 +633,11 @@ static int merge_lists(int64_t* launches, const uint64_t* d_lists, uint32_t n_li
   while (nl > fanin) {
     const uint32_t groups = (nl + fanin - 1) / fanin;
     uint64_t* dst = bufs[flip];
-    merge_topk_kernel<<<dim3(nq, groups), kMergeThreads, smem, st>>>(in, nl, fanin, nq, k, BUF, dst);
+    merge_topk_kernel<<<dim3(nq, groups), kMergeThreads, smem, st>>>(in, nl, fanin, nq, k, BUF, dst, list_stride);
     (*launches)++;
-    in = dst; nl = groups; flip ^= 1;
+    in = dst; nl = groups; flip ^= 1; list_stride = (uint64_t)nq * k;
   }
-  merge_topk_kernel<<<dim3(nq, 1), kMergeThreads, smem, st>>>(in, nl, nl, nq, k, BUF, d_out);
+  merge_topk_kernel<<<dim3(nq, 1), kMergeThreads, smem, st>>>(in, nl, nl, nq, k, BUF, d_out, list_stride);
   (*launches)++;
   CU(cudaGetLastError());
   return VC_OK;
@@ -749,8 +771,10 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &grid);
   if (rc) return rc;
   if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
-  bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, ident, nq, xhist);
-  bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, nullptr);
+  XchgDev nox;
+  memset(&nox, 0, sizeof nox);
+  bmih_settle_kernel<W><<<nq, 256, 0, st>>>(p, ident, nq, xhist, nox);
+  bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, nullptr, nox);
   ix->launches += 6;
   CU(cudaGetLastError());
   // any overflow?  (flags are written by the append path; one small read-back)
@@ -951,6 +975,46 @@ static uint64_t host_binom(uint32_t n, uint32_t r) {
   return c;
 }
 
+// ---- peer exchange (xchg.cuh) -------------------------------------------------------------------------------
+static uint64_t align16(uint64_t v) { return (v + 15) & ~(uint64_t)15; }
+static bool xchg_fits(const vc_index* ix, uint64_t bytes) { return ix->x_open && ix->x_enabled && align16(bytes) <= ix->x_slot_bytes; }
+// the next exchange: `bytes` per rank, published by `n_ctas` CTAs of the pushing kernel
+static XchgDev xchg_begin(vc_index* ix, uint64_t bytes, uint32_t n_ctas) {
+  XchgDev x;
+  memset(&x, 0, sizeof x);
+  for (uint32_t g = 0; g < ix->x_world; ++g) x.peer[g] = ix->x_peer[g];
+  x.rank = ix->x_rank; x.world = ix->x_world;
+  x.seq = ++ix->x_seq;
+  x.stride = align16(bytes);
+  x.slot_off = kXchgHeaderBytes + (uint64_t)(x.seq & 1u) * ix->x_world * ix->x_slot_bytes;
+  ix->x_done_total += n_ctas;
+  x.done = ix->x_ctr; x.done_target = ix->x_done_total; x.err = ix->x_ctr + 1;
+  ++ix->last_xchg;
+  return x;
+}
+static void xchg_push(vc_index* ix, const XchgDev& x, const void* d_src, uint64_t bytes, uint32_t grid, cudaStream_t st) {
+  xchg_push_kernel<<<grid, 256, 0, st>>>(x, (const uint4*)d_src, align16(bytes) / 16);
+  ix->launches++;
+}
+static uint32_t xchg_push_grid(const vc_index* ix, uint64_t bytes) {
+  return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ix->num_sms, (align16(bytes) / 16 + 255) / 256));
+}
+// Sum of the n_words u32 at d_words over all shards, in place: over peer memory when the windows are open and the payload
+// fits a slot, else through the caller's all-reduce hook (NCCL).  Every shard makes the same choice (same sizes everywhere).
+static int shard_allreduce(vc_index* ix, uint32_t* d_words, uint64_t n_words, cudaStream_t st) {
+  if (xchg_fits(ix, n_words * 4)) {
+    const uint32_t grid = xchg_push_grid(ix, n_words * 4);
+    const XchgDev x = xchg_begin(ix, n_words * 4, grid);
+    xchg_push(ix, x, d_words, n_words * 4, grid, st);
+    xchg_sum_kernel<<<grid, 256, 0, st>>>(x, d_words, n_words);
+    ix->launches++;
+    return VC_OK;
+  }
+  if (!ix->allreduce_fn) return fail(VC_ERR_STATE, "id-sharded search: the payload (%llu bytes) does not fit the exchange window and no all-reduce hook is set", (unsigned long long)(n_words * 4));
+  if (ix->allreduce_fn(ix->allreduce_user, d_words, n_words, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+  return VC_OK;
+}
+
 // exclusive scan of up to 2048 * 2048 u32 in place, no allocation (sums: >= ceil(n / 2048) words)
 static int scan_inplace_small(vc_index* ix, uint32_t* d, uint64_t n, uint32_t* sums, cudaStream_t st) {
   const uint64_t nb = (n + kScanTile - 1) / kScanTile;
@@ -1005,7 +1069,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.pair_count = (unsigned long long*)(ctr + 10);
   p.exec_pairs = (unsigned long long*)(ctr + 12);
   p.scan_mode = 0; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
-  p.gglobkey = ix->allreduce_fn ? (uint64_t*)(sb + o_globkey) : nullptr;
+  p.gglobkey = ix->sharded() ? (uint64_t*)(sb + o_globkey) : nullptr;
+  ix->last_xchg = 0;
+  XchgDev nox;
+  memset(&nox, 0, sizeof nox);
   p.boot_sample = (uint32_t)std::max<int64_t>(0, ix->mih_boot_sample);
   p.tc_stats = (unsigned long long*)(ctr + 16);
   const uint32_t popc_cpi = p.cpi;
@@ -1039,10 +1106,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   CU(cudaMemsetAsync(p.ghist, 0, (size_t)nq * Cfg::HB * 4, st));      // histograms count this search's candidates only
   CU(cudaMemsetAsync(xhist, 0, (size_t)nq * Cfg::HB * 4, st));
   bmih_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p, actA);
-  bmih_bootstrap_kernel<W><<<(nq + 7) / 8, 256, 0, st>>>(p, ix->allreduce_fn ? xhist : nullptr);
+  bmih_bootstrap_kernel<W><<<(nq + 7) / 8, 256, 0, st>>>(p, ix->sharded() ? xhist : nullptr);
   ix->launches += 2;
-  if (ix->allreduce_fn) {
-    if (ix->allreduce_fn(ix->allreduce_user, xhist, (uint64_t)nq * Cfg::HB, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+  if (ix->sharded()) {
+    if ((rc = shard_allreduce(ix, xhist, (uint64_t)nq * Cfg::HB, st))) return rc;
     bmih_boot_tau_kernel<W><<<(nq + 127) / 128, 128, 0, st>>>(p, xhist);
     ix->launches++;
   }
@@ -1152,19 +1219,27 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
     first_verify = false;
-    bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, xhist);
-    if (ix->allreduce_fn) {
-      // id-sharded search: sum the histograms over the shards, so that every GPU filters and stops on the k-th
-      // distance of the WHOLE database (and all ranks walk through the same steps)
-      if (ix->allreduce_fn(ix->allreduce_user, xhist, (uint64_t)nq * Cfg::HB, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+    // id-sharded search: the histograms are summed over the shards, so that every GPU filters and stops on the k-th
+    // distance of the WHOLE database (and all ranks walk through the same steps).  Over peer memory the settle kernel
+    // itself stores its rows into every shard's window and xchg_sum_kernel adds the G slots up; else the hook (NCCL).
+    if (ix->sharded() && xchg_fits(ix, (uint64_t)nq * Cfg::HB * 4)) {
+      const XchgDev x = xchg_begin(ix, (uint64_t)nq * Cfg::HB * 4, n_active);
+      bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, xhist, x);
+      xchg_sum_kernel<<<xchg_push_grid(ix, (uint64_t)nq * Cfg::HB * 4), 256, 0, st>>>(x, xhist, (uint64_t)nq * Cfg::HB);
+      ix->launches++;
+    } else {
+      bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, xhist, nox);
+      if (ix->sharded() && (rc = shard_allreduce(ix, xhist, (uint64_t)nq * Cfg::HB, st))) return rc;
     }
     bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
     if (timed) cudaEventRecord(ix->lev_x[2 * levels + 1], st);
     ix->launches += single_pass ? 6 : 7;
     CU(cudaGetLastError());
-    uint32_t h5[14];
+    uint32_t h5[14], x_err = 0;
     CU(cudaMemcpyAsync(h5, ctr, 56, cudaMemcpyDeviceToHost, st));
+    if (ix->x_open) CU(cudaMemcpyAsync(&x_err, ix->x_ctr + 1, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    if (x_err) return fail(VC_ERR_STATE, "peer exchange timed out: a shard did not arrive");
     {
       unsigned long long cc, pp, xx;
       memcpy(&cc, h5 + 8, 8); memcpy(&pp, h5 + 10, 8); memcpy(&xx, h5 + 12, 8);
@@ -1185,7 +1260,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       // next radius: one table at a time if most of the remaining queries would stop inside it anyway
       granular = max_radius < 0 && (ix->mih_table_steps > 0 || (ix->mih_table_steps < 0 && (uint64_t)n_likely * 2 >= n_active));
     }
-    if (ix->allreduce_fn && granular && n_active > 0 && r <= sbits && ix->mih_global_key != 0) {
+    if (ix->sharded() && granular && n_active > 0 && r <= sbits && ix->mih_global_key != 0) {
       // id-sharded search, next step one table of a radius: most queries' k-th distance now equals the distance bound of
       // what is left to find, so the k-th ID of the whole database decides what can still matter (bmih_idhist_kernel)
       const uint32_t lb_next = m * r + t0;
@@ -1194,14 +1269,23 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       uint32_t* idh = (uint32_t*)ix->b_idh.p;
       CU(cudaMemsetAsync(idh, 0, words * 4, st));
       bmih_idhist_kernel<<<(n_active * 32 + 255) / 256, 256, 0, st>>>(p, cur, n_active, lb_next, idh);
-      if (ix->allreduce_fn(ix->allreduce_user, idh, (uint64_t)words, (void*)st) != 0) return fail(VC_ERR_STATE, "all-reduce callback failed");
+      if ((rc = shard_allreduce(ix, idh, (uint64_t)words, st))) return rc;
       bmih_idcut_kernel<<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, lb_next, idh);
       ix->launches += 2;
     }
   }
   if (ix->profile) { ix->lev_used = std::min(levels, 34); ix->ev_valid = true; }
   (void)first_verify;
-  bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, d_stats);
+  // sharded call over peer memory (vc_search_sharded_dev): unless some query has to be redone below, the finish kernel
+  // itself stores the result rows into every shard's window
+  ix->x_pushed = false;
+  if (ix->x_fuse_finish && !h_ctr[3] && xchg_fits(ix, (uint64_t)nq * k * 8)) {
+    ix->x_finish = xchg_begin(ix, (uint64_t)nq * k * 8, nq);
+    bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, d_stats, ix->x_finish);
+    ix->x_pushed = true;
+  } else {
+    bmih_finish_kernel<<<nq, 128, 0, st>>>(p, d_out_keys, d_stats, nox);
+  }
   ix->launches++;
   if (ix->profile) cudaEventRecord(ix->ev_s1, st);
   if (h_ctr[3]) {
@@ -1243,7 +1327,7 @@ int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t
   const bool legal = ix->sbits <= 16 && !(approximate != 0 && max_radius < 0) && k < (uint32_t)kBmihSort / 2;
   // id-sharded (an all-reduce hook is set): only the batched path calls the hook, so the choice must not depend on this
   // shard's size - shard sizes differ by one code when N % G != 0, and one rank issuing collectives the others do not is a hang
-  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && (ix->allreduce_fn != nullptr || (ix->n >> ix->sbits) >= (uint64_t)ix->mih_min_bucket));
+  const bool want = ix->mih_batched > 0 || (ix->mih_batched < 0 && (ix->sharded() || (ix->n >> ix->sbits) >= (uint64_t)ix->mih_min_bucket));
   ix->last_mih_batched = 0;
   if (legal && want) {
     if (ix->W == 1) return mih_batched<1>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
@@ -1321,6 +1405,106 @@ int vc_nccl_allreduce_hook(void* user, uint32_t* d_words, uint64_t n_words, void
   return rc == 0 ? VC_OK : fail(VC_ERR_STATE, "ncclAllReduce failed (ncclResult_t %d)", rc);
 }
 
+// ---- peer exchange ---------------------------------------------------------------------------------------------
+int vc_xchg_create(vc_index* ix, uint32_t rank, uint32_t world, uint64_t slot_bytes, void* out_handle) {
+  if (!ix) return fail(VC_ERR_ARG, "null argument");
+  if (world < 2 || world > (uint32_t)kXchgMaxWorld || rank >= world) return fail(VC_ERR_ARG, "exchange of %u ranks (2 .. %d), rank %u", world, kXchgMaxWorld, rank);
+  if (ix->x_window) return fail(VC_ERR_STATE, "the exchange window exists already");
+  DeviceGuard g(ix->device);
+  slot_bytes = align16(std::max<uint64_t>(slot_bytes, 4096));
+  const uint64_t total = kXchgHeaderBytes + 2 * (uint64_t)world * slot_bytes;
+  CU(cudaMalloc((void**)&ix->x_window, total));
+  CU(cudaMemset(ix->x_window, 0, total));
+  CU(cudaMalloc((void**)&ix->x_ctr, 64));
+  CU(cudaMemset(ix->x_ctr, 0, 64));
+  CU(cudaDeviceSynchronize());
+  ix->x_rank = rank; ix->x_world = world; ix->x_slot_bytes = slot_bytes; ix->x_seq = 0; ix->x_done_total = 0; ix->x_open = false;
+  if (out_handle) {
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == VC_XCHG_HANDLE_BYTES, "IPC handle size");
+    CU(cudaIpcGetMemHandle(&h, ix->x_window));
+    memcpy(out_handle, &h, sizeof h);
+  }
+  return VC_OK;
+}
+
+int vc_xchg_local_window(vc_index* ix, void** window) {
+  if (!ix || !window) return fail(VC_ERR_ARG, "null argument");
+  if (!ix->x_window) return fail(VC_ERR_STATE, "no exchange window (vc_xchg_create)");
+  *window = ix->x_window;
+  return VC_OK;
+}
+
+int vc_xchg_open_ptrs(vc_index* ix, void* const* peer_windows) {
+  if (!ix || !peer_windows) return fail(VC_ERR_ARG, "null argument");
+  if (!ix->x_window) return fail(VC_ERR_STATE, "no exchange window (vc_xchg_create)");
+  for (uint32_t g = 0; g < ix->x_world; ++g) {
+    ix->x_peer[g] = g == ix->x_rank ? ix->x_window : (unsigned char*)peer_windows[g];
+    ix->x_ipc[g] = false;
+    if (!ix->x_peer[g]) return fail(VC_ERR_ARG, "window of rank %u is null", g);
+  }
+  ix->x_open = true;
+  return VC_OK;
+}
+
+int vc_xchg_open(vc_index* ix, const void* handles) {
+  if (!ix || !handles) return fail(VC_ERR_ARG, "null argument");
+  if (!ix->x_window) return fail(VC_ERR_STATE, "no exchange window (vc_xchg_create)");
+  DeviceGuard g(ix->device);
+  for (uint32_t r = 0; r < ix->x_world; ++r) {
+    if (r == ix->x_rank) { ix->x_peer[r] = ix->x_window; ix->x_ipc[r] = false; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * VC_XCHG_HANDLE_BYTES, sizeof h);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(VC_ERR_CUDA, "cudaIpcOpenMemHandle (window of rank %u): %s", r, cudaGetErrorString(e));
+    ix->x_peer[r] = (unsigned char*)ptr; ix->x_ipc[r] = true;
+  }
+  ix->x_open = true;
+  return VC_OK;
+}
+
+// One call = local search on this shard + exchange of the local top-k lists + merge: d_out_keys holds the answer over the
+// WHOLE database on every rank.  Over peer memory when the windows are open (the batched MIH search pushes its rows from
+// its last kernel, anything else through xchg_push_kernel); the caller falls back to its own all-gather otherwise.
+int vc_search_sharded_dev(vc_index* ix, int mih, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                          uint64_t* d_out_keys, void* stream) {
+  if (!ix || !d_queries || !d_out_keys) return fail(VC_ERR_ARG, "null argument");
+  if (nq == 0) return VC_OK;
+  const uint64_t bytes = (uint64_t)nq * k * 8;
+  if (!xchg_fits(ix, bytes)) return fail(VC_ERR_STATE, "the exchange windows are not open or too small for %llu bytes per rank", (unsigned long long)bytes);
+  DeviceGuard g(ix->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ix->x_local.ensure(bytes);
+  if (rc) return rc;
+  uint64_t* local = (uint64_t*)ix->x_local.p;
+  ix->x_fuse_finish = mih != 0;
+  ix->x_pushed = false;
+  rc = mih ? vc_search_mih_dev(ix, d_queries, nq, k, approximate, max_radius, local, nullptr, stream)
+           : vc_search_linear_dev(ix, d_queries, nq, k, local, stream);
+  ix->x_fuse_finish = false;
+  if (rc) return rc;
+  XchgDev x;
+  if (ix->x_pushed) {
+    x = ix->x_finish;
+  } else {
+    const uint32_t grid = xchg_push_grid(ix, bytes);
+    x = xchg_begin(ix, bytes, grid);
+    xchg_push(ix, x, local, bytes, grid, st);
+  }
+  xchg_wait_kernel<<<1, 32, 0, st>>>(x);
+  ix->launches++;
+  const uint64_t* slots = (const uint64_t*)(ix->x_peer[ix->x_rank] + x.slot_off);
+  rc = merge_lists(&ix->launches, slots, ix->x_world, nq, k, 1024, nullptr, nullptr, d_out_keys, st, x.stride / 8);
+  if (rc) return rc;
+  // a wait that timed out (a peer never arrived) must not pass as an answer
+  uint32_t err = 0;
+  CU(cudaMemcpyAsync(&err, ix->x_ctr + 1, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (err) return fail(VC_ERR_STATE, "peer exchange timed out: a shard did not arrive");
+  return VC_OK;
+}
+
 int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   if (!ix || !name) return fail(VC_ERR_ARG, "null argument");
   if (!strcmp(name, "scan.prefilter")) ix->scan_prefilter = value;
@@ -1344,6 +1528,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.tc")) ix->mih_tc = value;
   else if (!strcmp(name, "mih.tc_ratio")) ix->mih_tc_ratio = value;
   else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
+  else if (!strcmp(name, "xchg")) ix->x_enabled = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
   else if (!strcmp(name, "mih.cap")) {
     if (value < 0 || value > (1 << 20)) return fail(VC_ERR_ARG, "mih.cap must be in [0, 2^20]");
@@ -1397,6 +1582,9 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "mih.last_batched")) *value = ix->last_mih_batched;
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;
   else if (!strcmp(name, "mih.last_redo")) *value = ix->last_mih_redo;
+  else if (!strcmp(name, "xchg")) *value = ix->x_enabled;
+  else if (!strcmp(name, "xchg.open")) *value = ix->x_open ? 1 : 0;
+  else if (!strcmp(name, "xchg.last")) *value = ix->last_xchg;
   else if (!strcmp(name, "mih.last_items")) *value = ix->last_mih_items;
   else if (!strcmp(name, "mih.last_bucket_codes")) *value = ix->last_mih_bucket_codes;
   else if (!strncmp(name, "mih.step_exec.", 14)) {

@@ -23,6 +23,7 @@
 #pragma once
 #include "mih.cuh"
 #include "scan.cuh"
+#include "xchg.cuh"
 
 namespace vc {
 
@@ -307,9 +308,10 @@ struct __align__(16) BvWarp {
   uint32_t qid[kBmihQT];                 // their query indices
   uint32_t cut[kBmihQT];                 // their k-th ids (id cut of the last step of a search), or ~0
   uint32_t hitn, pad_[3];                // entries in hitq
+  uint8_t perm[kBmihQT];                 // scratch of the id cut: old staged slot -> new staged slot
   uint16_t hitq[kBmihHitQ];              // deferred hits: warp step of the item << 10 | lane << 5 | staged query slot
 };
-constexpr uint32_t kBvQid = kBmihQT * kBmihQSMax * 4, kBvCut = kBvQid + kBmihQT * 4, kBvHitN = kBvCut + kBmihQT * 4, kBvHitQ = kBvHitN + 16;
+constexpr uint32_t kBvQid = kBmihQT * kBmihQSMax * 4, kBvCut = kBvQid + kBmihQT * 4, kBvHitN = kBvCut + kBmihQT * 4, kBvHitQ = kBvHitN + 16 + kBmihQT;
 static_assert(sizeof(BvWarp) == kBvHitQ + kBmihHitQ * 2 && sizeof(BvWarp) % 16 == 0, "BvWarp layout");
 __shared__ BvWarp bv_warp[kBmihThreads / 32];
 __shared__ unsigned long long bv_pairs[kBmihThreads / 32];          // tests executed by the warp (statistics)
@@ -551,25 +553,35 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
         const bool keep = lane < qlive && w->cut[lane] > fid;
         const uint32_t alive = __ballot_sync(0xffffffffu, keep);
         if (!alive) break;
-        if (alive != (qlive >= 32 ? 0xFFFFFFFFu : ((1u << qlive) - 1u))) {
-          if (VC_HIT_QUEUE && *(volatile uint32_t*)&w->hitn) bmih_drain_hits<W, U4, QS>(&p, t, a0, c0, c1);     // queued hits name staged slots: before they move
+        const uint32_t live_mask = qlive >= 32 ? 0xFFFFFFFFu : ((1u << qlive) - 1u);
+        if (alive != live_mask) {
+          // The staged records are PARTITIONED, not dropped: the queries that go on move to the front, the ones that are done
+          // with this bucket behind them (slots >= the new qlive are not tested any more, but hits queued for them earlier in
+          // the item are still to be checked against their records), and the queued hits are renumbered accordingly.
+          const bool mine = lane < qlive;
+          const uint32_t gone = live_mask & ~alive;
+          const uint32_t pos = keep ? __popc(alive & ((1u << lane) - 1u)) : __popc(alive) + __popc(gone & ((1u << lane) - 1u));
           uint32_t rec[QS];
 #pragma unroll
-          for (int i = 0; i < QS; ++i) rec[i] = keep ? w->qrec[lane * QS + i] : 0u;
-          const uint32_t mq = keep ? w->qid[lane] : 0u, mc = keep ? w->cut[lane] : 0u;
+          for (int i = 0; i < QS; ++i) rec[i] = mine ? w->qrec[lane * QS + i] : 0u;
+          const uint32_t mq = mine ? w->qid[lane] : 0u, mc = mine ? w->cut[lane] : 0u;
           __syncwarp();
-          if (keep) {
-            const uint32_t pos = __popc(alive & ((1u << lane) - 1u));
+          if (mine) {
 #pragma unroll
             for (int i = 0; i < QS; ++i) w->qrec[pos * QS + i] = rec[i];
             w->qid[pos] = mq; w->cut[pos] = mc;
+          }
+          w->perm[lane] = (uint8_t)(mine ? pos : lane);
+          __syncwarp();
+          if (VC_HIT_QUEUE) {
+            const uint32_t nh = min(*(volatile uint32_t*)&w->hitn, (uint32_t)kBmihHitQ);
+            for (uint32_t i = lane; i < nh; i += 32) { const uint32_t e = w->hitq[i]; w->hitq[i] = (uint16_t)((e & ~31u) | w->perm[e & 31u]); }
           }
           qlive = __popc(alive);
           __syncwarp();
         }
         item_pairs += (min(c1, base + WSTEP) - max(base, c0)) * qlive;
       }
-      if (base != a0) load_step(base);
       if constexpr (kPfDist > 0) {
         // the codes kPfDist steps ahead on their way into L2 (a warp step is 2 KB = 16 lines; no registers needed)
         const uint32_t ahead = (base - a0 + kPfDist * WSTEP) * W / 2;
@@ -631,6 +643,9 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
           }
         }
       }
+      // the next step's codes start travelling now: the registers are free, and the rest of this step and the head of the next
+      // one hide (part of) the latency
+      if (base + WSTEP < c1) load_step(base + WSTEP);
       __syncwarp();
       if (refresh) {
         if (lane < qlive) {
@@ -661,13 +676,13 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
 // kept; the histogram row is also copied to `xhist`, which the decide kernel reads - possibly after it has been
 // summed over all id-shards (GPUs) by the caller's all-reduce.
 template <int W>
-__global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, uint32_t* xhist) {
+__global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, uint32_t* xhist, const XchgDev x) {
   __shared__ uint64_t buf[kBmihSort];
   __shared__ uint32_t cnt;
   __shared__ uint64_t s_tau;
   constexpr int HB = BmihCfg<W>::HB;
   const uint32_t tid = threadIdx.x;
-  if (blockIdx.x >= n_list) return;
+  if (blockIdx.x >= n_list) return;                       // (never true with a peer exchange: the grid is exactly n_list CTAs)
   const uint32_t q = list[blockIdx.x];
   const uint32_t raw = p.gcnt[q];
   const uint32_t n = min(raw, p.cap);
@@ -710,7 +725,15 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   // that after the cross-shard sum every shard takes the query out of the batched search at the same step (bmih_decide_kernel)
   if (tid == 0) sh[HB - 1] = p.gflag[q] & 1u;
   __syncthreads();
-  for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = sh[i];
+  if (x.world) {
+    // id-sharded over peer memory (xchg.cuh): the row goes straight into slot [rank] of every shard's window; xchg_sum_kernel
+    // then leaves the sum over the shards in xhist
+    const uint64_t off = x.slot_off + (uint64_t)x.rank * x.stride + (uint64_t)q * HB * 4;
+    for (uint32_t i = tid; i < HB; i += 256)
+      for (uint32_t g = 0; g < x.world; ++g) reinterpret_cast<uint32_t*>(x.peer[g] + off)[i] = sh[i];
+  } else {
+    for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = sh[i];
+  }
   if (tid == 0) {
     uint32_t* gc = p.ghist + (size_t)q * HB;
     uint32_t cum = 0;
@@ -721,6 +744,7 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
     p.gtaukey[q] = p.gglobkey ? min(tk, p.gglobkey[q]) : tk;
     if (tk != kEmptyKey) atomicMin(&p.gtau[q], (uint32_t)(tk >> 32));
   }
+  if (x.world) xchg_publish(x);
 }
 
 // ---- 5. decide: stop rule and next active list ------------------------------------------------------------
@@ -952,16 +976,26 @@ __global__ void __launch_bounds__(256) scan_bootstrap_kernel(const BmihParams p,
   if (tid == 0 && s_bound != kInfDist) p.gtau[q] = s_bound;
 }
 
-__global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_query_stats* stats) {
+// With a peer exchange (x.world > 0, id-sharded search) the row also goes straight into slot [rank] of every shard's window:
+// the all-gather of the local top-k lists is this kernel's own stores (xchg.cuh), the merge kernel follows after the wait.
+__global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_query_stats* stats, const XchgDev x) {
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t kept = min(p.gcnt[q], p.k);
-  for (uint32_t i = tid; i < p.k; i += blockDim.x) out_keys[(size_t)q * p.k + i] = i < kept ? p.gbuf[(size_t)q * p.cap + i] : kEmptyKey;
+  for (uint32_t i = tid; i < p.k; i += blockDim.x) {
+    const uint64_t key = i < kept ? p.gbuf[(size_t)q * p.cap + i] : kEmptyKey;
+    out_keys[(size_t)q * p.k + i] = key;
+    if (x.world) {
+      const uint64_t off = x.slot_off + (uint64_t)x.rank * x.stride + ((uint64_t)q * p.k + i) * 8;
+      for (uint32_t g = 0; g < x.world; ++g) *reinterpret_cast<uint64_t*>(x.peer[g] + off) = key;
+    }
+  }
   if (stats && tid == 0) {
     vc_query_stats st;
     st.radius = p.gradius[q]; st.n_results = kept; st.probes = p.gprobes[q]; st.occupancy_tests = 0;
     st.candidates = p.gcands[q]; st.unique = 0;
     stats[q] = st;
   }
+  if (x.world) xchg_publish(x);
 }
 
 // queries whose candidate buffer overflowed: listed for the per-query kernel, which writes their rows of the output itself

@@ -385,9 +385,10 @@ __global__ void scan_init_kernel(uint32_t* gtau, uint32_t* ghist, uint32_t nq, u
 constexpr int kMergeThreads = 256;
 
 // grid = (nq, groups): group g folds lists [g*fanin, min((g+1)*fanin, n_lists)) into out[g][q][0..k)
+// list_stride = keys between list l and list l + 1 (nq * k when the lists are contiguous)
 __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_t* __restrict__ lists, uint32_t n_lists, uint32_t fanin,
                                                                    uint32_t nq, uint32_t k, uint32_t BUF,
-                                                                   uint64_t* __restrict__ out) {
+                                                                   uint64_t* __restrict__ out, uint64_t list_stride) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* buf = (uint64_t*)smem_raw;            // [BUF]
   __shared__ uint32_t cnt;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
     const uint64_t i = base + tid;
     if (i < total) {
       const uint64_t l = l0 + i / k, j = i % k;
-      const uint64_t key = lists[(l * nq + q) * k + j];
+      const uint64_t key = lists[l * list_stride + (uint64_t)q * k + j];
       if (key < tau_s) { uint32_t slot = atomicAdd(&cnt, 1u); buf[slot] = key; }   // kEmptyKey never passes
     }
     __syncthreads();

@@ -13,9 +13,13 @@ flag once per radius step (src/mpi_coordinator.cc:26-69, src/search_worker.cc:17
     the shards (vc_index_set_allreduce), so that every GPU filters and stops on the k-th distance of the
     WHOLE database: a shard then does 1/G of the single-GPU work instead of searching to its own, larger,
     local k-th distance.  (The reference exchanges all candidates and a stop flag per radius step.)
-    These per-step exchanges are issued by the library itself - ncclAllReduce on the search stream, from C
-    (vc_nccl_allreduce_hook) - on a communicator created here; VC_NCCL_DIRECT=0 routes them through
-    torch.distributed.all_reduce instead (a Python callback per exchange).
+  * on NVLink-connected GPUs neither exchange goes through NCCL: every rank opens the others' exchange windows (CUDA IPC,
+    handles carried by torch.distributed) and the search kernels store their histogram rows and top-k rows straight into
+    the peers' memory (verticut_b200/csrc/xchg.cuh; one call, Index.search_sharded_dev, = search + exchange + merge).
+    VC_XCHG=0 turns that off; the exchanges then go to ncclAllReduce issued by the library from C on the search stream
+    (vc_nccl_allreduce_hook, a communicator created here; VC_NCCL_DIRECT=0: torch.distributed.all_reduce through a Python
+    callback), and the results to torch's all_gather_into_tensor + the merge kernel.  Payloads larger than a window slot
+    take that route too.
 
 torch.distributed is plumbing here (process group, the all-gather, device buffers); searching and
 merging are the library's CUDA kernels, called through the C ABI with raw device pointers.
@@ -69,6 +73,7 @@ class ShardedSearcher:
         self._bufs = {}
         self._views = {}
         self._nccl = None
+        self.peer_windows = False
         self.exchange = "none"
         if self.world > 1 and global_threshold and hasattr(index, "set_allreduce"):
             index.set_allreduce(self._allreduce_words)
@@ -76,6 +81,8 @@ class ShardedSearcher:
             if os.environ.get("VC_NCCL_DIRECT", "1") != "0" and hasattr(index, "set_allreduce_nccl") and dist.get_backend(group) == "nccl":
                 self._nccl_direct()
                 self.exchange = "ncclAllReduce from C on the search stream"
+            if os.environ.get("VC_XCHG", "1") != "0" and hasattr(index, "xchg_create") and dist.get_backend(group) == "nccl":
+                self._open_peer_windows()
 
     def _nccl_direct(self):
         """The library's per-step exchanges call ncclAllReduce themselves (vc_nccl_allreduce_hook), on the search stream, on a
@@ -103,6 +110,37 @@ class ShardedSearcher:
             raise RuntimeError("ncclCommInitRank failed (ncclResult_t %d)" % rc)
         self._nccl = (nccl, comm)                          # keep the library handle and the communicator alive
         self.index.set_allreduce_nccl(C.cast(nccl.ncclAllReduce, C.c_void_p).value, comm.value)
+
+    XCHG_SLOT_BYTES = 16 << 20      # largest payload of one rank in one exchange that goes over peer memory (else: NCCL)
+
+    def _open_peer_windows(self):
+        """Exchange windows over NVLink peer memory: allocate mine, hand its IPC handle to the peers, open theirs.  If any rank
+        cannot (no peer access between the devices), every rank stays on the NCCL path."""
+        t, dist = self.torch, self.dist
+        dev = t.device("cuda", self.index.device)
+        ok, handle = 1, bytes(capi.XCHG_HANDLE_BYTES)
+        try:
+            handle = self.index.xchg_create(self.rank, self.world, self.XCHG_SLOT_BYTES)
+        except capi.VerticutError:
+            ok = 0
+        mine = t.tensor(list(handle), dtype=t.uint8, device=dev)
+        everyone = t.empty(self.world * capi.XCHG_HANDLE_BYTES, dtype=t.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        flag = t.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()):
+            try:
+                self.index.xchg_open(bytes(everyone.cpu().tolist()))
+            except capi.VerticutError:
+                ok = 0
+            flag = t.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.peer_windows = bool(int(flag.item()))
+        if self.peer_windows:
+            self.exchange = "stores into the peers' memory over NVLink (xchg.cuh), NCCL only for payloads above %d MB" % (self.XCHG_SLOT_BYTES >> 20)
+        else:
+            self.index.set_param("xchg", 0)
+        dist.barrier(group=self.group)
 
     def close(self):
         """Releases the library's own NCCL communicator (if any); the index is the caller's."""
@@ -169,6 +207,13 @@ class ShardedSearcher:
         packed words (bit pattern of uint64, ascending), identical on every rank."""
         nq = d_queries.shape[0]
         local, gathered, merged = self._buffers(nq, k, d_queries.device)
+        if self.peer_windows and nq * k * 8 <= self.XCHG_SLOT_BYTES and mode in ("mih", "linear"):
+            # search + exchange + merge in one call, the exchange being the search kernels' own stores into the peers' windows
+            if mode == "mih":
+                self.index.set_param("mih.boot_sample", max(2048, max(16384, 16 * k) // self.world))
+            self.index.search_sharded_dev(mode == "mih", d_queries.data_ptr(), nq, k, merged.data_ptr(), approximate=approximate,
+                                          max_radius=max_radius, stream=self._stream(d_queries.device))
+            return merged
         self.local_search(d_queries, k, mode, approximate, max_radius, local)
         if self.world == 1:
             return local
