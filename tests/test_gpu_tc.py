@@ -109,3 +109,33 @@ def test_tc_mih_large_batch_matches_popc_kernel(oracle, bits, m, n, nq):
     np.testing.assert_array_equal(a[0][:8], lid)
     np.testing.assert_array_equal(a[1][:8], ld)
     ix.close()
+
+
+@pytest.mark.parametrize("bits", [64, 128, 256])
+@pytest.mark.parametrize("n,nq,k", [(1000, 3, 10), (5000, 17, 100), (70001, 40, 10), (300000, 5, 100), (40_000, 300, 10)])
+def test_tc_v1_scan_matches_oracle(oracle, bits, n, nq, k):
+    """The first version of the tensor-core kernel (tcverify_v1.cuh, "scan.tc" = 2: A operand through shared memory, up to 256
+    queries per tile) - the one that measured faster than the POPC kernel on large scan batches."""
+    lin.EXTRA_PARAMS = {"scan.tc": 2}
+    lin._run(oracle, n, bits, nq, k)
+
+
+def test_tc_v1_scan_edge_cases_and_large(oracle):
+    lin.EXTRA_PARAMS = {"scan.tc": 2}
+    lin._run(oracle, 50_000, 64, 7, 100, first_id=4_000_000_000 - 50_000)
+    lin._run(oracle, 7, 64, 3, 10)
+    lin._run(oracle, 129, 64, 257, 10)
+    lin.test_linear_heavy_ties(oracle)
+    n, nq, k = 4_000_000, 520, 100
+    ix = capi.Index(64, 0)
+    ix.add_synthetic(n, 12345)
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    ix.set_param("scan.batched", 1)
+    ix.set_param("scan.tc", 2)
+    a = ix.search_linear(queries, k)
+    assert ix.get_param("scan.last_tc") == 1 and ix.get_param("scan.last_batched") == 1
+    ix.set_param("scan.tc", 0)
+    b = ix.search_linear(queries, k)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    ix.close()

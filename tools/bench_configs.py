@@ -1,6 +1,9 @@
-"""One-GPU measurements of the BASELINE.json configs that are not the bench.py headline (C1, C2, C3-per-GPU-shard, C5),
-each checked for self-consistency (MIH == linear scan on the same index) on a few queries.
-    python tools/bench_configs.py > profiles/configs_r01.json"""
+"""One-GPU measurements that bench.py --config does not cover: C1 (the reference's own CPU-runnable case) on the GPU, the sparse
+(s = 32) variant of C5, and the reference's NATIVE shape - 128-bit codes, 4 tables of 32-bit substrings, 100 M codes, k = 100
+(src/run_distributed_search.py:8-12, src/image_search_constants.h:14) - as a fixed-radius sweep (on uniform codes its exact k-NN
+needs radius 9, i.e. 1.7 * 10^8 bitmap probes per query: not a workload) beside the brute-force scan of the same
+index.  Each exact case is checked for self-consistency (MIH == linear scan on the same index) on a few queries.
+    python tools/bench_configs.py > profiles/configs_r02.json        (C2 - C5 at full size: bench.py --config ...)"""
 import json
 import os
 import sys
@@ -91,11 +94,9 @@ if __name__ == "__main__":
         sys.exit(0)
     res = []
     res.append(run("C1 linear 1M x 64-bit, 1k queries, k=10 (GPU; MIH m=4 beside it)", 1_000_000, 64, 4, 10, 1000, scan_batches=(1000,)))
-    res.append(run("C2 MIH 64-bit m=4, 100M codes, k=100", 100_000_000, 64, 4, 100, 4096))
-    res.append(run("C3 shard: MIH 128-bit m=8, 125M codes (1/8 of 1B), k=100", 125_000_000, 128, 8, 100, 1024))
     for r in (0, 1, 2, 3):
-        res.append(run("C5 (reduced N to fit one GPU) MIH 256-bit m=16, 60M codes, k=1000, fixed radius %d" % r, 60_000_000, 256, 16,
-                       1000, 256, max_radius=r, scan_batches=(1,) if r == 0 else ()))
+        res.append(run("reference's native shape: 128-bit, m=4 (s=32 bitmap tables), 100M codes, k=100, fixed radius %d" % r, 100_000_000, 128, 4,
+                       100, 1024, max_radius=r, scan_batches=(1, 1024) if r == 0 else ()))
     res.append(run("C5 sparse: MIH 256-bit m=8 (s=32 bitmap tables), 60M codes, k=1000, fixed radius 2", 60_000_000, 256, 8, 1000, 64,
                    max_radius=2, scan_batches=()))
     print(json.dumps(res, indent=1))

@@ -17,6 +17,7 @@
 #include "scan.cuh"
 #include "bmih.cuh"
 #include "tcverify.cuh"
+#include "tcverify_v1.cuh"
 #include "xchg.cuh"
 
 using namespace vc;
@@ -112,7 +113,7 @@ struct vc_index {
   int64_t scan_waves = 0;         // 0 auto
   int64_t scan_stages = 0;        // 0 auto: ring depth
   int64_t scan_batched = -1;        // large batches through the verify kernel: -1 auto, 0 never, 1 always
-  int64_t scan_batched_min = 8;
+  int64_t scan_batched_min = 2;     // measured on 1 B x 64-bit codes: batch 2 / 4 reach 0.93 / 0.87 of the HBM peak through the verify kernel, 0.74 / 0.63 through the ring kernel
   int64_t last_scan_batched = 0;
   int64_t scan_ctas_per_sm = 2;    // shared-memory plan targets this many resident CTAs per SM
   int64_t scan_interleave = 1;    // slices interleaved step-wise (1) or contiguous (0)
@@ -701,6 +702,21 @@ template <int W>
 static int launch_bmih_verify_tc_any(const BmihParams& p, int num_sms, cudaStream_t st) {
   return launch_bmih_verify_tc<W, 128>(p, num_sms, st);
 }
+// the first version of the tensor-core kernel (tcverify_v1.cuh: A operand through shared memory, 4 expander warps, up to 256
+// queries per tile): "scan.tc" / "mih.tc" = 2.  The faster of the two on large scan batches (profiles/tc_r02.md).
+template <int W, int QT>
+static int launch_bmih_verify_tc1(const BmihParams& p, int num_sms, cudaStream_t st) {
+  using Cfg = Tc1Cfg<W, QT>;
+  CU(cudaFuncSetAttribute(bmih_verify_tc1_kernel<W, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  bmih_verify_tc1_kernel<W, QT><<<num_sms, kTc1Threads, Cfg::SMEM, st>>>(p);
+  return VC_OK;
+}
+template <int W> constexpr uint32_t tc1_max_qt() { return W == 4 ? 128u : 256u; }
+template <int W>
+static int launch_bmih_verify_tc1_any(const BmihParams& p, int num_sms, cudaStream_t st) {
+  if constexpr (W == 4) return p.qt > 64 ? launch_bmih_verify_tc1<4, 128>(p, num_sms, st) : launch_bmih_verify_tc1<4, 64>(p, num_sms, st);
+  else return p.qt > 64 ? launch_bmih_verify_tc1<W, 256>(p, num_sms, st) : launch_bmih_verify_tc1<W, 64>(p, num_sms, st);
+}
 template <int W> constexpr uint32_t tc_max_qt() { return 128u; }
 
 static int search_linear_ring(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, cudaStream_t st);
@@ -743,8 +759,9 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   p.qlist = ident;
   // >= scan.tc_min queries per code: the distance filter goes to the tensor cores (tcverify.cuh)
   const bool use_tc = ix->scan_tc > 0 || (ix->scan_tc < 0 && nq >= (uint32_t)ix->scan_tc_min);
+  const bool tc_v1 = ix->scan_tc == 2 || ix->scan_tc < 0;       // by size: the version that measured faster than the POPC kernel
   p.cpi = use_tc ? kTcCpi : 8 * Cfg::STEP;
-  p.qt = use_tc ? tc_max_qt<W>() : (uint32_t)kBmihQT;
+  p.qt = use_tc ? (tc_v1 ? (nq > 64 ? tc1_max_qt<W>() : 64u) : tc_max_qt<W>()) : (uint32_t)kBmihQT;
   ix->last_scan_tc = use_tc ? 1 : 0;
   const uint64_t n = ix->n;
   const uint32_t nc = (uint32_t)((n + p.cpi - 1) / p.cpi), nqc = (nq + p.qt - 1) / p.qt;
@@ -767,7 +784,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
     CU(cudaMemsetAsync(ix->b_trace.p, 0, 3 * 256 * 4 * 8, st));
     p.tc_trace = (long long*)ix->b_trace.p;
   }
-  if (use_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
+  if (use_tc) rc = tc_v1 ? launch_bmih_verify_tc1_any<W>(p, ix->num_sms, st) : launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
   else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &grid);
   if (rc) return rc;
   if (ix->profile) { cudaEventRecord(ix->ev1, st); ix->ev_valid = true; ix->lev_used = 0; }
@@ -833,8 +850,8 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   if (nq == 0) return VC_OK;
   DeviceGuard g(ix->device);
   cudaStream_t st = (cudaStream_t)stream;
-  // small batches are HBM-bound: the TMA-ring kernel streams the shard once at ~0.94 of the copy peak; larger
-  // batches are POPC-bound and go through the warp-granular verify kernel
+  // a single query is HBM-bound: the TMA-ring kernel streams the shard once at ~0.91 of the copy peak; batches go through
+  // the warp-granular verify kernel (HBM-bound up to ~4 queries, POPC-bound above)
   // (candidates appended per query ~ 15-20 k before the thresholds settle: automatic only while that fits the buffer)
   const bool batched = ix->scan_batched > 0 || (ix->scan_batched < 0 && nq >= (uint32_t)ix->scan_batched_min && k <= 128);
   ix->last_scan_batched = 0;

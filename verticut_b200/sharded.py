@@ -111,7 +111,7 @@ class ShardedSearcher:
         self._nccl = (nccl, comm)                          # keep the library handle and the communicator alive
         self.index.set_allreduce_nccl(C.cast(nccl.ncclAllReduce, C.c_void_p).value, comm.value)
 
-    XCHG_SLOT_BYTES = 16 << 20      # largest payload of one rank in one exchange that goes over peer memory (else: NCCL)
+    XCHG_SLOT_BYTES = 32 << 20      # largest payload of one rank in one exchange that goes over peer memory (else: NCCL)
 
     def _open_peer_windows(self):
         """Exchange windows over NVLink peer memory: allocate mine, hand its IPC handle to the peers, open theirs.  If any rank
