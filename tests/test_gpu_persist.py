@@ -42,3 +42,38 @@ def test_load_rejects_garbage(tmp_path):
     p.write_bytes(b"not an index at all")
     with pytest.raises(capi.VerticutError):
         capi.Index.load(str(p))
+
+
+@pytest.mark.parametrize("bits,m", [(64, 4), (64, 2)])
+def test_load_rejects_a_corrupt_bucket_directory(tmp_path, oracle, bits, m):
+    """A file whose row_ptr (dense tables) or occupancy bitmap (s = 32) was damaged must be refused at load time: every search
+    kernel trusts those arrays for its addresses."""
+    n = 20_000
+    codes = oracle.synth_codes(12345, 0, n, bits // 8)
+    ix = capi.Index(bits, m)
+    ix.add(codes)
+    ix.build()
+    path = tmp_path / "index.vc"
+    ix.save(str(path))
+    ix.close()
+    raw = bytearray(path.read_bytes())
+    header, table_header = 40, 16
+    first_table = header + n * (bits // 8) + table_header          # first row_ptr entry of table 0
+    # dense: a bucket start beyond the code count; sparse: the same (row_ptr comes first in both layouts)
+    bad = bytearray(raw)
+    bad[first_table + 4 * 100: first_table + 4 * 100 + 4] = (0x7FFFFFFF).to_bytes(4, "little")
+    p1 = tmp_path / "bad1.vc"
+    p1.write_bytes(bytes(bad))
+    with pytest.raises(capi.VerticutError):
+        capi.Index.load(str(p1))
+    if bits // m == 32:
+        # flip one bit of the occupancy bitmap: popcount and rank directory no longer agree with the header
+        n_unique = int.from_bytes(raw[header + n * (bits // 8) + 4: header + n * (bits // 8) + 8], "little")
+        bitmap_off = first_table + 4 * (n_unique + 1)
+        bad = bytearray(raw)
+        bad[bitmap_off + 12345] ^= 0x10
+        p2 = tmp_path / "bad2.vc"
+        p2.write_bytes(bytes(bad))
+        with pytest.raises(capi.VerticutError):
+            capi.Index.load(str(p2))
+    capi.Index.load(str(path)).close()                               # the undamaged file still loads

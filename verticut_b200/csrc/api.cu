@@ -126,11 +126,14 @@ struct vc_index {
   int64_t mih_min_bucket = 64;
   uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
   int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(16384, 16 k))
+  int64_t mih_split_r0 = 0;       // 1: radius 0 is a search step of its own (tighter thresholds for radius 1) instead of being probed together with radius 1
   int64_t mih_cap = 0;            // candidate-buffer entries per query (0: bmih_cap_for(k)); small values force the overflow path in tests
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
   // tensor-core verify kernel (tcverify.cuh): 0 never (default: measured slower than the POPC kernels),
   // 1 whenever legal, -1 by size (scan: >= scan.tc_min queries; MIH: steps with >= mih.tc_ratio queries per code)
-  int64_t scan_tc = 0, scan_tc_min = 48, last_scan_tc = 0;
+  // scan: -1 by default = the first version of the kernel (tcverify_v1.cuh, = 2) for 64-bit codes and >= scan.tc_min queries, where it
+  // measured 1.13 - 1.16 x the POPC kernel (profiles/tc_r02.md); MIH: 0 (a probed bucket is shared by too few queries to fill a tile)
+  int64_t scan_tc = -1, scan_tc_min = 256, last_scan_tc = 0;
   int64_t mih_tc = 0, mih_tc_ratio = 10, last_mih_tc_steps = 0;
   int64_t tc_trace = 0;           // debug: dump CTA 0's pipeline timestamps of the last tensor-core launch to stderr
   DevBuf b_trace;
@@ -558,6 +561,31 @@ int vc_index_load(int device, const char* path, vc_index** out) {
     if (e == cudaSuccess) e = cudaMemcpy(ix->d_tab, ix->tab, sizeof(TableDev) * kMaxTables, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = fail(VC_ERR_CUDA, "table descriptors: %s", cudaGetErrorString(e));
   }
+  if (!rc && h.m) {
+    // nothing of the file is trusted before it has been checked on the device
+    uint32_t* d_bad = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_bad, 16);
+    if (e == cudaSuccess) e = cudaMemset(d_bad, 0, 16);
+    for (uint32_t t = 0; t < h.m && e == cudaSuccess; ++t) {
+      const TableDev& T = ix->tab[t];
+      const uint64_t entries = T.sparse ? (uint64_t)T.n_unique + 1 : (1ull << h.sbits) + 1;
+      validate_row_ptr_kernel<<<grid_for(entries, 256, ix->num_sms), 256>>>(T.row_ptr, entries, h.n, d_bad);
+      if (T.sparse) {
+        const uint64_t nrb = (1ull << h.sbits) / kRankBlockBits;
+        CU(cudaMemset(d_bad + 2, 0, 8));
+        validate_bitmap_kernel<<<grid_for(nrb, 256, ix->num_sms), 256>>>(T.bitmap, T.rank_dir, nrb, (unsigned long long*)(d_bad + 2), d_bad);
+        unsigned long long bits = 0;
+        e = cudaMemcpy(&bits, d_bad + 2, 8, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && bits != T.n_unique) rc = fail(VC_ERR_ARG, "corrupt index file: table %u has %llu occupied buckets, header says %u", t, bits, T.n_unique);
+      }
+      ix->launches += T.sparse ? 2 : 1;
+    }
+    uint32_t bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, 4, cudaMemcpyDeviceToHost);
+    if (d_bad) cudaFree(d_bad);
+    if (e != cudaSuccess) rc = fail(VC_ERR_CUDA, "index validation: %s", cudaGetErrorString(e));
+    else if (!rc && bad) rc = fail(VC_ERR_ARG, "corrupt index file: a bucket directory is not a non-decreasing sequence ending at the code count");
+  }
   if (rc) { vc_index_destroy(ix); return rc; }
   ix->built = true; ix->max_bucket_len = 0;
   *out = ix;
@@ -758,7 +786,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   uint32_t* xhist = (uint32_t*)(sb + o_xhist);
   p.qlist = ident;
   // >= scan.tc_min queries per code: the distance filter goes to the tensor cores (tcverify.cuh)
-  const bool use_tc = ix->scan_tc > 0 || (ix->scan_tc < 0 && nq >= (uint32_t)ix->scan_tc_min);
+  const bool use_tc = ix->scan_tc > 0 || (ix->scan_tc < 0 && W == 1 && nq >= (uint32_t)ix->scan_tc_min && k <= 128);
   const bool tc_v1 = ix->scan_tc == 2 || ix->scan_tc < 0;       // by size: the version that measured faster than the POPC kernel
   p.cpi = use_tc ? kTcCpi : 8 * Cfg::STEP;
   p.qt = use_tc ? (tc_v1 ? (nq > 64 ? tc1_max_qt<W>() : 64u) : tc_max_qt<W>()) : (uint32_t)kBmihQT;
@@ -853,7 +881,10 @@ int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint3
   // a single query is HBM-bound: the TMA-ring kernel streams the shard once at ~0.91 of the copy peak; batches go through
   // the warp-granular verify kernel (HBM-bound up to ~4 queries, POPC-bound above)
   // (candidates appended per query ~ 15-20 k before the thresholds settle: automatic only while that fits the buffer)
-  const bool batched = ix->scan_batched > 0 || (ix->scan_batched < 0 && nq >= (uint32_t)ix->scan_batched_min && k <= 128);
+  // (2 .. 7 queries only on shards of >= 4 GB: the batched path has ~0.5 ms of fixed work in front of its kernel - threshold
+  // bootstrap, settle, one host read-back of the overflow flags - which a 0.3 ms scan of a small shard does not pay back)
+  const bool batched = ix->scan_batched > 0 || (ix->scan_batched < 0 && k <= 128 &&
+                       (nq >= 8 || (nq >= (uint32_t)ix->scan_batched_min && ix->n * ix->W * 8 >= (4ull << 30))));
   ix->last_scan_batched = 0;
   if (batched && k < (uint32_t)kBmihSort / 2 && ix->n > 0 && ix->n < 0xFFFFFFFFull) {
     if (ix->W == 1) return scan_batched<1>(ix, d_queries, nq, k, d_out_keys, st);
@@ -1148,7 +1179,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     // radius 0 alone can only end a search whose k-th distance is below m; in the adaptive rhythm it is probed
     // together with radius 1 (one step less; its few, long work items overlap with radius 1's many)
     const uint32_t r_lo = r;
-    if (r == 0 && !granular && ix->mih_table_steps < 0 && sbits >= 1 && max_radius != 0) r = 1;
+    if (r == 0 && !granular && ix->mih_table_steps < 0 && sbits >= 1 && max_radius != 0 && !ix->mih_split_r0) r = 1;
     p.radius = r; p.r_lo = r_lo; p.t_begin = t0; p.t_end = t1; p.active = cur; p.n_active = n_active; p.next_active = nxt;
     const bool timed = ix->profile && levels < 34;
     if (timed) {
@@ -1228,8 +1259,11 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     if (timed) cudaEventRecord(ix->lev[2 * levels], st);
     // few queries per probed bucket (radii 0 and 1): the step is not POPC-bound, and the exact distance as the filter sends
     // far fewer codes down the slow path than the one-POPC lower bound does (4.22 -> 4.05 ms at 1 B codes, batch 4096)
+    // ... and so do the steps that start at radius 0 whatever the batch: their thresholds come straight from the bootstrap
+    // (3 - 4 above the final k-th distance), where the lower bound passes a third of the lane-records (batch 16384, radii 0 + 1:
+    // 13.5 ms with the lower bound)
     const bool pf_auto = ix->mih_prefilter < 0;
-    const bool pf = pf_all && !(pf_auto && W == 1 && total_probes < 2 * ((uint64_t)(t1 - t0) << sbits));
+    const bool pf = pf_all && !(pf_auto && W == 1 && (r_lo == 0 || total_probes < 2 * ((uint64_t)(t1 - t0) << sbits)));
     if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
     else if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
     else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &verify_grid);
@@ -1547,6 +1581,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
   else if (!strcmp(name, "xchg")) ix->x_enabled = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
+  else if (!strcmp(name, "mih.split_r0")) ix->mih_split_r0 = value;
   else if (!strcmp(name, "mih.cap")) {
     if (value < 0 || value > (1 << 20)) return fail(VC_ERR_ARG, "mih.cap must be in [0, 2^20]");
     ix->mih_cap = value;

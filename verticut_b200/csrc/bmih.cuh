@@ -57,12 +57,6 @@ constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (s
 #ifndef VC_TAU_EVERY
 #define VC_TAU_EVERY 1
 #endif
-#ifndef VC_PAIRS_PER_ITEM
-#define VC_PAIRS_PER_ITEM 0
-#endif
-#ifndef VC_APPEND_OVERLAP
-#define VC_APPEND_OVERLAP 0
-#endif
 constexpr int kPfDist = VC_PF_DIST;  // L2 prefetch distance of the verify kernel, in warp steps of 2 KB
 
 template <int W, int U4 = kBmihU4> struct BmihCfg {

@@ -225,6 +225,29 @@ __global__ void gather_payload_kernel(const uint64_t* __restrict__ main_codes, c
   }
 }
 
+// A table read back from a file (vc_index_load) before any kernel trusts it: row_ptr non-decreasing and ending at n; for a
+// sparse table also popcount(bitmap) == n_unique and rank_dir = exclusive prefix sums of the 256-bit block counts.
+// bad[0] is raised on any violation (a truncated or corrupt file would otherwise mean out-of-bounds reads in every search).
+__global__ void validate_row_ptr_kernel(const uint32_t* __restrict__ row_ptr, uint64_t entries, uint64_t n, uint32_t* bad) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < entries; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = row_ptr[i];
+    if (v > n || (i + 1 < entries && row_ptr[i + 1] < v) || (i == 0 && v != 0) || (i + 1 == entries && v != n)) atomicOr(bad, 1u);
+  }
+}
+__global__ void validate_bitmap_kernel(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ rank_dir, uint64_t n_blocks,
+                                       unsigned long long* total, uint32_t* bad) {
+  // rank_dir[b] must equal the set bits before block b: checked locally (rank_dir[b + 1] - rank_dir[b] == bits of block b)
+  unsigned long long mine = 0;
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < n_blocks; b += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t c = 0;
+    for (uint32_t w = 0; w < kRankBlockBits / 32; ++w) c += __popc(bitmap[b * (kRankBlockBits / 32) + w]);
+    mine += c;
+    if (b == 0 && rank_dir[0] != 0) atomicOr(bad, 1u);
+    if (b + 1 < n_blocks && rank_dir[b + 1] - rank_dir[b] != c) atomicOr(bad, 1u);
+  }
+  if (mine) atomicAdd(total, mine);
+}
+
 template <int W>
 __global__ void synth_codes_kernel(uint64_t* __restrict__ codes, uint64_t n, uint64_t first_id, uint64_t id_stride, uint64_t seed) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * W; i += (uint64_t)gridDim.x * blockDim.x)
