@@ -126,6 +126,7 @@ struct vc_index {
   int64_t mih_min_bucket = 64;
   uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
   int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(16384, 16 k))
+  int64_t mih_r0_first = 0;       // a step that probes radius 0 together with radius 1 verifies the radius-0 buckets first
   int64_t mih_split_r0 = 0;       // 1: radius 0 is a search step of its own (tighter thresholds for radius 1) instead of being probed together with radius 1
   int64_t mih_cap = 0;            // candidate-buffer entries per query (0: bmih_cap_for(k)); small values force the overflow path in tests
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
@@ -1092,7 +1093,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
                o_xhist = take((size_t)nq * Cfg::HB * 4), o_globkey = take((size_t)nq * 8),
                o_ctr = take(128);   // [0] n_items [1] item_cursor [2] n_next [3] any_overflow [4] n_likely [8..9] bucket_codes
   if ((rc = ix->b_state.ensure(off))) return rc;
-  if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024))) return rc;
+  if ((rc = ix->b_buckets.ensure(((size_t)n_buckets * 2 + 2 + kScanTile) * 4 + 1024 + n_buckets))) return rc;
   unsigned char* sb = (unsigned char*)ix->b_state.p;
   uint32_t* ctr = (uint32_t*)(sb + o_ctr);            // [0] n_items  [1] item_cursor  [2] n_next  [3] any_overflow
   BmihParams p;
@@ -1112,6 +1113,8 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   const bool wide = ix->mih_wide > 0;   // measured slower than the 8-codes-per-thread variant at 3 CTAs/SM; kept as a knob
   p.bcount = (uint32_t*)ix->b_buckets.p; p.boffs = p.bcount + n_buckets;
   uint32_t* scan_sums = p.boffs + n_buckets + 1 + 3;
+  uint8_t* bflag = (uint8_t*)(scan_sums + kScanTile + 64);
+  const bool r0_first = ix->mih_r0_first != 0;
   p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
   p.bucket_codes = (unsigned long long*)(ctr + 8);
   p.pair_count = (unsigned long long*)(ctr + 10);
@@ -1197,6 +1200,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     p.qlist = (uint32_t*)ix->b_qlist.p;
     const int pgrid = grid_for(total_probes, 256, ix->num_sms);
     CU(cudaMemsetAsync(p.bcount, 0, (size_t)n_buckets * 4, st));
+    // a step that probes radius 0 together with higher radii: the queries' own buckets are verified first (bmih_items_kernel)
+    const bool two_phase = r0_first && r_lo == 0 && r > 0 && !tc_possible;
+    p.bflag = two_phase ? bflag : nullptr;
+    if (two_phase) CU(cudaMemsetAsync(bflag, 0, n_buckets, st));
     bmih_probe_kernel<W><<<pgrid, 256, 0, st>>>(p, 0);
     CU(cudaMemcpyAsync(p.boffs, p.bcount, (size_t)n_buckets * 4, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemsetAsync(p.boffs + n_buckets, 0, 4, st));
@@ -1255,7 +1262,13 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     CU(cudaMemsetAsync(ctr, 0, 12, st));
     CU(cudaMemsetAsync(ctr + 4, 0, 4, st));
     p.count_in_write = single_pass ? 1u : 0u;
-    bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
+    if (two_phase) {
+      bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1, 0);
+      bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1, 1);
+      ix->launches++;
+    } else {
+      bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
+    }
     if (timed) cudaEventRecord(ix->lev[2 * levels], st);
     // few queries per probed bucket (radii 0 and 1): the step is not POPC-bound, and the exact distance as the filter sends
     // far fewer codes down the slow path than the one-POPC lower bound does (4.22 -> 4.05 ms at 1 B codes, batch 4096)
@@ -1582,6 +1595,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "xchg")) ix->x_enabled = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
   else if (!strcmp(name, "mih.split_r0")) ix->mih_split_r0 = value;
+  else if (!strcmp(name, "mih.r0_first")) ix->mih_r0_first = value;
   else if (!strcmp(name, "mih.cap")) {
     if (value < 0 || value > (1 << 20)) return fail(VC_ERR_ARG, "mih.cap must be in [0, 2^20]");
     ix->mih_cap = value;

@@ -91,6 +91,7 @@ struct BmihParams {
   uint32_t n_active;
   uint32_t* bcount;             // [m << sbits] queries per bucket (pass 0), then cursor (pass 1)
   uint32_t* boffs;              // [(m << sbits) + 1] exclusive scan of bcount
+  uint8_t* bflag;               // [m << sbits] or null: 1 = the bucket is probed at radius 0 by some query of this step (its work items go first)
   uint32_t* qlist;              // [total probes] query index per (bucket, slot)
   BmihItem* items;
   uint32_t* n_items;            // [1]
@@ -131,7 +132,7 @@ __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
   for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; base < total; base += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t it = base + lane;
     const bool valid = it < total;
-    uint32_t q = 0xFFFFFFFFu, len = 0, b = 0;
+    uint32_t q = 0xFFFFFFFFu, len = 0, b = 0, key = 0, qkey_of_probe = 1;
     if (valid) {
       const uint32_t a = (uint32_t)(it / per_q);
       const uint32_t rem = (uint32_t)(it % per_q);
@@ -140,13 +141,15 @@ __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
       while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
       q = p.active[a];
       const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
-      const uint32_t key = qkey ^ unrank_mask(p.sbits, rad, pidx);
+      key = qkey ^ unrank_mask(p.sbits, rad, pidx);
+      qkey_of_probe = qkey;
       const uint32_t* rp = p.tables[t].row_ptr;
       len = rp[key + 1] - rp[key];
       b = (t << p.sbits) + key;
     }
     if (pass == 0) {
       if (len) atomicAdd(&p.bcount[b], 1u);
+      if (len && p.bflag && key == qkey_of_probe) p.bflag[b] = 1;
       if (__any_sync(0xffffffffu, len >= (1u << 26))) {         // giant buckets (degenerate data): 32-bit warp sums could wrap
         if (len) { atomicAdd(&p.gcands[q], (unsigned long long)len); atomicAdd(p.pair_count, (unsigned long long)len); }
       } else {
@@ -178,8 +181,11 @@ __global__ void bmih_maxlen_kernel(const TableDev* tables, uint32_t m, uint32_t 
 
 // ---- 2. work items -------------------------------------------------------------------------------------------
 // write = 0: only count the items (n_items); write = 1: emit descriptors at atomically claimed positions
+// phase (with p.bflag): 0 = only the buckets probed at radius 0, 1 = only the others, 2 = all.  A step that starts at radius 0 emits
+// its items in two launches, 0 then 1: the queries' own buckets hold their nearest candidates, and with those verified first the
+// thresholds have tightened before the bulk of the step (the radius-1 buckets) is streamed.
 template <int W>
-__global__ void bmih_items_kernel(const BmihParams p, int write) {
+__global__ void bmih_items_kernel(const BmihParams p, int write, int phase = 2) {
   const uint32_t n_buckets = p.m << p.sbits;
   const uint32_t lane = threadIdx.x & 31;
   // whole warps walk the bucket list: item positions are claimed with one atomic per warp (prefix sum over the lanes),
@@ -189,6 +195,7 @@ __global__ void bmih_items_kernel(const BmihParams p, int write) {
     uint32_t cnt = 0, len = 0, t = 0, key = 0, nc = 0, nqc = 0, alt = 0;
     const uint32_t* rp = nullptr;
     if (b < n_buckets) cnt = p.boffs[b + 1] - p.boffs[b];
+    if (cnt && phase != 2 && (p.bflag[b] != 0) != (phase == 0)) cnt = 0;
     if (cnt) {
       t = b >> p.sbits; key = b & ((1u << p.sbits) - 1);
       rp = p.tables[t].row_ptr;
