@@ -136,9 +136,14 @@ int vc_search_mih(vc_index* ix, const void* queries, uint32_t nq, uint32_t k, in
 
 /* ---- search, device buffers (multi-GPU plumbing and zero-copy callers) ----------------------
  * d_queries / d_out_keys live on the index's device; d_out_keys is [nq][k] packed words
- * (VC_EMPTY_KEY padded), ascending.  `stream` is a cudaStream_t (NULL = default stream).  The linear
- * scan only enqueues work; the MIH search walks its radius steps from the host and synchronises the
- * stream between them (it reads back a few counters per step).  d_stats may be NULL. */
+ * (VC_EMPTY_KEY padded), ascending.  `stream` is a cudaStream_t (NULL = default stream).  Neither call is
+ * asynchronous: the MIH search walks its radius steps from the host and synchronises the stream between them
+ * (it reads back a few counters per step); the linear scan only enqueues work for a single query, but a batch
+ * goes through the batched kernels, which end with one stream synchronisation and a read-back of the per-query
+ * overflow flags (a query whose candidate buffer overflowed - adversarial ties - is re-run by the ring kernel).
+ * d_stats may be NULL.  In an id-sharded search (vc_index_set_allreduce / vc_xchg_open) every rank must make the
+ * same calls in the same order; an error on one rank in the middle of a search (out of memory, a failing hook)
+ * leaves the other ranks' exchanges unmatched and is fatal for the communicator / ends in the exchange's time-out. */
 int vc_search_linear_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, void* stream);
 int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
                       uint64_t* d_out_keys, vc_query_stats* d_stats, void* stream);

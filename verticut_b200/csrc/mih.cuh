@@ -19,8 +19,9 @@
 //   * top-k: canonical (dist,id) order; per-warp staging buffers are folded into one sorted
 //     per-query buffer under a shared-memory lock, so memory stays bounded whatever the ties.
 //   * stop rule: m-aware and strict, d_k <= m*(r+1) - 1, which makes the result identical to a
-//     full scan (SURVEY.md findings 6, 7).  No collective per radius step: each GPU applies the
-//     rule to its own id-shard.
+//     full scan (SURVEY.md findings 6, 7).  This per-query kernel applies it to its own id-shard
+//     (no exchange); the batched path (bmih.cuh) sums the shards' distance histograms once per step
+//     and stops on the k-th distance of the whole database.
 #pragma once
 #include "build.cuh"
 #include "../../include/verticut_gpu.h"
