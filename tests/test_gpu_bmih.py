@@ -166,3 +166,16 @@ def test_batched_settle_folds_more_candidates_than_fit_in_shared_memory(oracle):
     np.testing.assert_array_equal(ids, oid)
     np.testing.assert_array_equal(dists, od)
     ix.close()
+
+
+@pytest.mark.parametrize("knobs", [{"mih.r0_first": 1}, {"mih.split_r0": 1}, {"mih.r0_first": 1, "mih.prefilter": 1}, {"mih.prefilter": 0}],
+                         ids=["r0_first", "split_r0", "r0_first+lower-bound", "exact-filter"])
+@pytest.mark.parametrize("n,bits,m,nq,k", [(300_000, 64, 4, 40, 100), (120_000, 128, 8, 12, 100), (40_000, 256, 16, 6, 50)])
+def test_batched_first_step_variants_are_exact(oracle, knobs, n, bits, m, nq, k):
+    """How the first search step is organised (the queries' own buckets verified first / radius 0 as a step of its own / which
+    filter) changes thresholds and order of discovery, never the answer."""
+    base.EXTRA_PARAMS = dict(knobs)
+    try:
+        base._check_exact(oracle, n, bits, m, nq, k)
+    finally:
+        base.EXTRA_PARAMS = {}

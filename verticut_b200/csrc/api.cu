@@ -771,6 +771,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   memset(&p, 0, sizeof p);
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = 1; p.sbits = 0; p.max_radius = 0; p.cap = cap;
   p.scan_mode = 1; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
+  p.pf_tau = ix->scan_prefilter > 0 ? 0x7FFFFFFFu : bmih_pf_tau(W, 0, true);
   TableDev pseudo;
   memset(&pseudo, 0, sizeof pseudo);
   pseudo.codes = ix->d_codes;
@@ -1120,6 +1121,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.pair_count = (unsigned long long*)(ctr + 10);
   p.exec_pairs = (unsigned long long*)(ctr + 12);
   p.scan_mode = 0; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
+  p.pf_tau = ix->mih_prefilter > 0 ? 0x7FFFFFFFu : bmih_pf_tau(W, sbits, false);
   p.gglobkey = ix->sharded() ? (uint64_t*)(sb + o_globkey) : nullptr;
   ix->last_xchg = 0;
   XchgDev nox;
@@ -1270,13 +1272,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
     }
     if (timed) cudaEventRecord(ix->lev[2 * levels], st);
-    // few queries per probed bucket (radii 0 and 1): the step is not POPC-bound, and the exact distance as the filter sends
-    // far fewer codes down the slow path than the one-POPC lower bound does (4.22 -> 4.05 ms at 1 B codes, batch 4096)
-    // ... and so do the steps that start at radius 0 whatever the batch: their thresholds come straight from the bootstrap
-    // (3 - 4 above the final k-th distance), where the lower bound passes a third of the lane-records (batch 16384, radii 0 + 1:
-    // 13.5 ms with the lower bound)
-    const bool pf_auto = ix->mih_prefilter < 0;
-    const bool pf = pf_all && !(pf_auto && W == 1 && (r_lo == 0 || total_probes < 2 * ((uint64_t)(t1 - t0) << sbits)));
+    // 64- and 128-bit codes: the lower-bound filter, which the kernel swaps for the exact distance record by record while a
+    // threshold is still loose (bmih_pf_tau); 256-bit codes: the exact distance throughout (the OR bound does not reject at
+    // the thresholds of config C5)
+    const bool pf = pf_all;
     if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
     else if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
     else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &verify_grid);

@@ -21,6 +21,7 @@
 // that the candidate buffers stay small from the first level on.  A query whose candidate buffer overflows
 // all the same (adversarial ties) is re-run by the per-query kernel, so the result is exact whatever the data.
 #pragma once
+#include <math.h>
 #include "mih.cuh"
 #include "scan.cuh"
 #include "xchg.cuh"
@@ -43,7 +44,7 @@ constexpr int kBmihU4 = VC_U4;           // 128-bit loads per thread per step (s
 #define VC_VERIFY_CTAS 4   // 64-bit codes: 4 CTAs (32 warps, 64 registers) per SM - the kernel is latency-bound, 15.5 instead of 16.7 ms per search
 #endif
 #ifndef VC_VERIFY_CTAS_W2
-#define VC_VERIFY_CTAS_W2 3   // 128- and 256-bit codes: not re-measured at 4 CTAs per SM yet
+#define VC_VERIFY_CTAS_W2 4   // 128- and 256-bit codes: 4 CTAs per SM (64 registers) measured 5 % faster than 3 (80) on C3 and C5 (profiles/ab_r02.md)
 #endif
 #ifndef VC_KEY_SUBST
 #define VC_KEY_SUBST 1       // bucket key substituted into the staged queries (a sharper one-POPC-per-64-bit filter), see bmih_verify_kernel
@@ -77,6 +78,7 @@ struct BmihParams {
   uint32_t t_begin, t_end;      // ... and its tables [t_begin, t_end): a whole radius (0, m) or one table of it
   uint32_t cpi;                 // codes per work item (multiple of the step size)
   uint32_t cap;                 // candidate-buffer entries per query (bmih_cap_for(k))
+  uint32_t pf_tau;              // PREFILTER kernels: staged thresholds >= this are tested on the exact distance (see bmih_pf_tau)
   uint32_t boot_sample;         // codes per query the threshold bootstrap looks at (0: the default)
   uint32_t count_in_write;      // items kernel: the writing pass is the only pass, it also keeps the statistics
   uint32_t qt;                  // queries per work item (kBmihQT for the POPC kernel, up to 256 for the tensor-core kernel)
@@ -248,6 +250,18 @@ __host__ __device__ inline uint32_t bmih_cap_for(uint32_t k) {
   uint32_t cap = kBmihCapMin;
   while (cap < 8u * k) cap <<= 1;
   return cap;
+}
+
+// The lower-bound filter popc(x_lo | x_hi) costs half the POPCs of the exact distance but passes more codes: on random bits it is
+// ~ N(mean, var) with 0.75 per OR-ed position and 0.5 per position whose partner is the substituted substring (VC_KEY_SUBST).
+// Every pass costs the hit path ~ 10 clocks, the exact filter 8 more POPCs = 64 clocks per warp-record of 256 tests: the lower
+// bound pays while fewer than ~ 6 of 256 pass, i.e. below mean - 2.2 sigma.  Above that (thresholds fresh from the bootstrap, first
+// search step) the kernel tests the exact distance - decided per staged record, a warp-uniform branch.
+__host__ inline uint32_t bmih_pf_tau(uint32_t W, uint32_t sbits, bool scan_mode) {
+  const double s = scan_mode || !VC_KEY_SUBST ? 0.0 : (double)sbits;
+  const double dbl = 32.0 * W - s, mean = 0.75 * dbl + 0.5 * s, var = 0.1875 * dbl + 0.25 * s;
+  const double t = mean - 2.2 * sqrt(var);
+  return t < 1.0 ? 1u : (uint32_t)t;
 }
 
 // rare path: a code whose exact distance d passed the staged threshold tau_s of query qid.
@@ -600,14 +614,14 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       auto test_query = [&](const QRec<W>& cur, uint32_t q) {
         const uint32_t tau = cur.tau;
         uint32_t mn;
-        if constexpr (C >= 3) {
-          mn = PREFILTER ? hamming_lower_bound<W>(code[0].w, cur.qw) : hamming_exact<W>(code[0].w, cur.qw);
+        if (PREFILTER && tau < p.pf_tau) {
+          mn = hamming_lower_bound<W>(code[0].w, cur.qw);
 #pragma unroll
-          for (int c = 1; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
+          for (int c = 1; c < C; ++c) mn = min(mn, hamming_lower_bound<W>(code[c].w, cur.qw));
         } else {
-          mn = 0xFFFFFFFFu;
+          mn = hamming_exact<W>(code[0].w, cur.qw);
 #pragma unroll
-          for (int c = 0; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
+          for (int c = 1; c < C; ++c) mn = min(mn, hamming_exact<W>(code[c].w, cur.qw));
         }
 #if VC_HIT_QUEUE
         if (mn <= tau) {
