@@ -1175,6 +1175,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   int levels = 0;
   int64_t items_total = 0;
   bool first_verify = true;
+  bool loose_majority = true;           // thresholds straight from the bootstrap
   // steps: (radius r, tables [t0, t1)).  A whole radius per step, or - when most queries are about to stop - one
   // table per step, so that the strict rule d_k <= m*r + t can end the search in the middle of a radius.
   uint32_t r = 0, t0 = 0;
@@ -1263,6 +1264,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     p.items = (BmihItem*)ix->b_items.p;
     CU(cudaMemsetAsync(ctr, 0, 12, st));
     CU(cudaMemsetAsync(ctr + 4, 0, 4, st));
+    CU(cudaMemsetAsync(ctr + 14, 0, 4, st));
     p.count_in_write = single_pass ? 1u : 0u;
     if (two_phase) {
       bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1, 0);
@@ -1272,10 +1274,12 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1);
     }
     if (timed) cudaEventRecord(ix->lev[2 * levels], st);
-    // 64- and 128-bit codes: the lower-bound filter, which the kernel swaps for the exact distance record by record while a
-    // threshold is still loose (bmih_pf_tau); 256-bit codes: the exact distance throughout (the OR bound does not reject at
-    // the thresholds of config C5)
-    const bool pf = pf_all;
+    // Which filter: the one-POPC-per-64-bit lower bound - unless most queries' thresholds are still too loose for it (fresh from
+    // the bootstrap; counted by the decide kernel, bmih_pf_tau), or the step has fewer than two queries per probed bucket (it is
+    // HBM-bound then, and the exact distance sends fewer codes down the hit path); 256-bit codes: the exact distance throughout
+    // (the OR bound does not reject at the thresholds of config C5).
+    const bool pf_auto = ix->mih_prefilter < 0;
+    const bool pf = pf_all && !(pf_auto && (loose_majority || total_probes < 2 * ((uint64_t)(t1 - t0) << sbits)));
     if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
     else if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
     else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &verify_grid);
@@ -1294,12 +1298,12 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
       bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, xhist, nox);
       if (ix->sharded() && (rc = shard_allreduce(ix, xhist, (uint64_t)nq * Cfg::HB, st))) return rc;
     }
-    bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4);
+    bmih_decide_kernel<W><<<(n_active + 127) / 128, 128, 0, st>>>(p, cur, n_active, xhist, ctr + 3, ctr + 4, ctr + 14);
     if (timed) cudaEventRecord(ix->lev_x[2 * levels + 1], st);
     ix->launches += single_pass ? 6 : 7;
     CU(cudaGetLastError());
-    uint32_t h5[14], x_err = 0;
-    CU(cudaMemcpyAsync(h5, ctr, 56, cudaMemcpyDeviceToHost, st));
+    uint32_t h5[16], x_err = 0;
+    CU(cudaMemcpyAsync(h5, ctr, 64, cudaMemcpyDeviceToHost, st));
     if (ix->x_open) CU(cudaMemcpyAsync(&x_err, ix->x_ctr + 1, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (x_err) return fail(VC_ERR_STATE, "peer exchange timed out: a shard did not arrive");
@@ -1314,6 +1318,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     if (single_pass) n_items = h5[0];
     const uint32_t n_likely = h5[4];
     n_active = h5[2];
+    loose_majority = (uint64_t)h5[14] * 2 >= n_active;
     std::swap(cur, nxt);
     ++levels;
     items_total += n_items;

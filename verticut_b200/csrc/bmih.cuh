@@ -78,7 +78,7 @@ struct BmihParams {
   uint32_t t_begin, t_end;      // ... and its tables [t_begin, t_end): a whole radius (0, m) or one table of it
   uint32_t cpi;                 // codes per work item (multiple of the step size)
   uint32_t cap;                 // candidate-buffer entries per query (bmih_cap_for(k))
-  uint32_t pf_tau;              // PREFILTER kernels: staged thresholds >= this are tested on the exact distance (see bmih_pf_tau)
+  uint32_t pf_tau;              // thresholds (less the probing radius) >= this count as loose: the lower-bound filter would pass too much (bmih_pf_tau)
   uint32_t boot_sample;         // codes per query the threshold bootstrap looks at (0: the default)
   uint32_t count_in_write;      // items kernel: the writing pass is the only pass, it also keeps the statistics
   uint32_t qt;                  // queries per work item (kBmihQT for the POPC kernel, up to 256 for the tensor-core kernel)
@@ -255,8 +255,10 @@ __host__ __device__ inline uint32_t bmih_cap_for(uint32_t k) {
 // The lower-bound filter popc(x_lo | x_hi) costs half the POPCs of the exact distance but passes more codes: on random bits it is
 // ~ N(mean, var) with 0.75 per OR-ed position and 0.5 per position whose partner is the substituted substring (VC_KEY_SUBST).
 // Every pass costs the hit path ~ 10 clocks, the exact filter 8 more POPCs = 64 clocks per warp-record of 256 tests: the lower
-// bound pays while fewer than ~ 6 of 256 pass, i.e. below mean - 2.2 sigma.  Above that (thresholds fresh from the bootstrap, first
-// search step) the kernel tests the exact distance - decided per staged record, a warp-uniform branch.
+// bound pays while fewer than ~ 6 of 256 pass, i.e. below mean - 2.2 sigma.  A search step whose queries are mostly above that
+// (thresholds fresh from the bootstrap: the first step for 64-bit codes, radii 0 - 2 for 128-bit codes at 125 M codes) runs the
+// kernel variant that filters on the exact distance; bmih_decide_kernel counts the loose queries for the host's choice.  (Decided
+// per step, not per record: a warp-uniform branch per record in the distance loop cost 4 - 8 % in the steps that do not need it.)
 __host__ inline uint32_t bmih_pf_tau(uint32_t W, uint32_t sbits, bool scan_mode) {
   const double s = scan_mode || !VC_KEY_SUBST ? 0.0 : (double)sbits;
   const double dbl = 32.0 * W - s, mean = 0.75 * dbl + 0.5 * s, var = 0.1875 * dbl + 0.25 * s;
@@ -614,14 +616,14 @@ __global__ void __launch_bounds__(kBmihThreads, U4 > 4 ? 2 : (W == 1 ? VC_VERIFY
       auto test_query = [&](const QRec<W>& cur, uint32_t q) {
         const uint32_t tau = cur.tau;
         uint32_t mn;
-        if (PREFILTER && tau < p.pf_tau) {
-          mn = hamming_lower_bound<W>(code[0].w, cur.qw);
+        if constexpr (C >= 3) {
+          mn = PREFILTER ? hamming_lower_bound<W>(code[0].w, cur.qw) : hamming_exact<W>(code[0].w, cur.qw);
 #pragma unroll
-          for (int c = 1; c < C; ++c) mn = min(mn, hamming_lower_bound<W>(code[c].w, cur.qw));
+          for (int c = 1; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
         } else {
-          mn = hamming_exact<W>(code[0].w, cur.qw);
+          mn = 0xFFFFFFFFu;
 #pragma unroll
-          for (int c = 1; c < C; ++c) mn = min(mn, hamming_exact<W>(code[c].w, cur.qw));
+          for (int c = 0; c < C; ++c) mn = min(mn, PREFILTER ? hamming_lower_bound<W>(code[c].w, cur.qw) : hamming_exact<W>(code[c].w, cur.qw));
         }
 #if VC_HIT_QUEUE
         if (mn <= tau) {
@@ -771,7 +773,7 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
 // the per-radius form d_k <= m*(r+1) - 1).  With summed histograms every shard takes the same decisions.
 template <int W>
 __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uint32_t n_list, const uint32_t* xhist,
-                                   uint32_t* any_overflow, uint32_t* n_likely) {
+                                   uint32_t* any_overflow, uint32_t* n_likely, uint32_t* n_loose) {
   constexpr int HB = BmihCfg<W>::HB;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_list) return;
@@ -799,7 +801,13 @@ __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uin
   // would this query stop somewhere inside the next radius even if tau did not improve any more?
   if (!stop && level_done && tau != kInfDist && tau + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
   if (stop) atomicOr(&p.gflag[q], 2u);
-  else p.next_active[atomicAdd(p.n_next, 1u)] = q;
+  else {
+    p.next_active[atomicAdd(p.n_next, 1u)] = q;
+    // the next step probes at radius r (more tables of this radius) or r + 1: is this query's threshold, less that radius, still
+    // too loose for the lower-bound filter?
+    const uint32_t r_next = level_done ? r + 1 : r;
+    if (__ldcg(&p.gtau[q]) >= p.pf_tau + r_next) atomicAdd(n_loose, 1u);
+  }
 }
 
 // ---- id-sharded search: a bound on the k-th KEY of the whole database ------------------------------------------
