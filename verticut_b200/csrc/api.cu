@@ -126,7 +126,9 @@ struct vc_index {
   int64_t mih_min_bucket = 64;
   uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
   int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(16384, 16 k))
-  int64_t mih_r0_first = 0;       // a step that probes radius 0 together with radius 1 verifies the radius-0 buckets first
+  // a step that probes radius 0 together with radius 1 verifies the queries' own (radius-0) buckets first, on the exact distance, and
+  // the other buckets after them with the lower-bound filter: -1 = when the step has >= 2 queries per probed bucket, 0 never, 1 always
+  int64_t mih_r0_first = -1;
   int64_t mih_split_r0 = 0;       // 1: radius 0 is a search step of its own (tighter thresholds for radius 1) instead of being probed together with radius 1
   int64_t mih_cap = 0;            // candidate-buffer entries per query (0: bmih_cap_for(k)); small values force the overflow path in tests
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
@@ -1115,7 +1117,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   p.bcount = (uint32_t*)ix->b_buckets.p; p.boffs = p.bcount + n_buckets;
   uint32_t* scan_sums = p.boffs + n_buckets + 1 + 3;
   uint8_t* bflag = (uint8_t*)(scan_sums + kScanTile + 64);
-  const bool r0_first = ix->mih_r0_first != 0;
+  const int64_t r0_first = ix->mih_r0_first;
   p.qlist = nullptr; p.items = nullptr; p.n_items = ctr; p.item_cursor = ctr + 1; p.n_next = ctr + 2;
   p.bucket_codes = (unsigned long long*)(ctr + 8);
   p.pair_count = (unsigned long long*)(ctr + 10);
@@ -1204,7 +1206,8 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     const int pgrid = grid_for(total_probes, 256, ix->num_sms);
     CU(cudaMemsetAsync(p.bcount, 0, (size_t)n_buckets * 4, st));
     // a step that probes radius 0 together with higher radii: the queries' own buckets are verified first (bmih_items_kernel)
-    const bool two_phase = r0_first && r_lo == 0 && r > 0 && !tc_possible;
+    const bool two_phase = r_lo == 0 && r > 0 && !tc_possible && pf_all &&
+                           (r0_first > 0 || (r0_first < 0 && total_probes >= 2 * ((uint64_t)(t1 - t0) << sbits)));
     p.bflag = two_phase ? bflag : nullptr;
     if (two_phase) CU(cudaMemsetAsync(bflag, 0, n_buckets, st));
     bmih_probe_kernel<W><<<pgrid, 256, 0, st>>>(p, 0);
@@ -1268,6 +1271,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     p.count_in_write = single_pass ? 1u : 0u;
     if (two_phase) {
       bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1, 0);
+      CU(cudaMemcpyAsync(ctr + 15, ctr, 4, cudaMemcpyDeviceToDevice, st));      // items of the radius-0 buckets: [0, ctr[15])
       bmih_items_kernel<W><<<igrid, 256, 0, st>>>(p, 1, 1);
       ix->launches++;
     } else {
@@ -1280,7 +1284,18 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     // (the OR bound does not reject at the thresholds of config C5).
     const bool pf_auto = ix->mih_prefilter < 0;
     const bool pf = pf_all && !(pf_auto && (loose_majority || total_probes < 2 * ((uint64_t)(t1 - t0) << sbits)));
-    if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
+    if (two_phase && ix->mih_prefilter < 0 && !wide) {
+      // the queries' own buckets hold their nearest candidates: verified first, on the exact distance (thresholds are fresh from
+      // the bootstrap); after them every threshold is the query's radius-0 k-th distance, tight enough for the lower bound
+      BmihParams p0 = p;
+      p0.n_items = ctr + 15;
+      rc = launch_bmih_verify<W, false, kBmihU4>(p0, ix->num_sms, st, &verify_grid);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(ctr + 1, ctr + 15, 4, cudaMemcpyDeviceToDevice, st));   // the cursor continues behind them
+      rc = launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid);
+      ix->launches++;
+    }
+    else if (step_tc) rc = launch_bmih_verify_tc_any<W>(p, ix->num_sms, st);
     else if (wide) rc = pf ? launch_bmih_verify<W, true, 8>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, 8>(p, ix->num_sms, st, &verify_grid);
     else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &verify_grid);
     if (rc) return rc;
