@@ -1,6 +1,8 @@
 """P5 on one GPU: the database cut into G id-shards (G index objects), per-shard search, merge kernel ==
 the unsharded search == the oracle.  (The NCCL all-gather itself is covered by bench.py --gpus N and by the
 gloo test of the plumbing.)"""
+import os
+
 import numpy as np
 import pytest
 
@@ -198,60 +200,70 @@ def test_two_shards_with_live_exchange(oracle, table_steps):
     np.testing.assert_array_equal(md, od)
 
 
-def test_two_shards_over_peer_windows(oracle):
-    """The peer-memory exchange (verticut_b200/csrc/xchg.cuh) between two shards on ONE GPU: each shard's window is opened by
-    the other through its device pointer (vc_xchg_open_ptrs), two host threads search at the same time on two streams; the settle
-    kernel's histogram rows and the finish kernel's top-k rows go through the windows, vc_search_sharded_dev returns the merged
-    answer on both "ranks".  Merged result == oracle, exactly, for the MIH search, the linear scan and a fixed-radius search."""
-    import threading
+def _peer_rank(rank, G, n, nq, k, conns, ret):
+    """One id-shard in its own process, on GPU 0: window handles travel through pipes, searches through vc_search_sharded_dev."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch
-    n, nq, k, G = 1_200_000, 48, 100, 2
-    codes = oracle.synth_codes(12345, 0, n, 8)
-    queries = oracle.synth_codes(67890, 0, nq, 8)
+    from oracle import restatement as R
+    from verticut_b200 import capi as C2
+    queries = R.synth_codes(67890, 0, nq, 8)
     dq = torch.from_numpy(queries).cuda()
-    ixs = []
-    for g in range(G):
-        first, stride, cnt = shard_interleaved(n, G, g)
-        ix = capi.Index(64, 4, first_id=first)
-        ix.set_param("id_stride", stride)
-        ix.add_synthetic(cnt, 12345)
-        ix.build()
-        ix.set_param("mih.batched", 1)
-        ix.search_mih(queries, k)                       # every scratch buffer of the unsharded path exists before the threads start
-        ix.search_linear(queries, k)
-        ixs.append(ix)
-    for g in range(G):
-        ixs[g].xchg_create(g, G, 4 << 20)
-    wins = [ix.xchg_local_window() for ix in ixs]
-    for g in range(G):
-        ixs[g].xchg_open_ptrs(wins)
+    first, stride, cnt = shard_interleaved(n, G, rank)
+    ix = C2.Index(64, 4, first_id=first)
+    ix.set_param("id_stride", stride)
+    ix.add_synthetic(cnt, 12345)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    mine = ix.xchg_create(rank, G, 4 << 20)
+    for c in conns:                                     # full exchange of the 64-byte IPC handles
+        c.send((rank, mine))
+    handles = {rank: mine}
+    for c in conns:
+        r, h = c.recv()
+        handles[r] = h
+    ix.xchg_open(b"".join(handles[r] for r in range(G)))
+    outs = [torch.empty((nq, k), dtype=torch.int64, device="cuda") for _ in range(3)]
+    ix.search_sharded_dev(True, dq.data_ptr(), nq, k, outs[0].data_ptr())
+    n_x = ix.get_param("xchg.last")
+    ix.search_sharded_dev(False, dq.data_ptr(), nq, k, outs[1].data_ptr())
+    ix.search_sharded_dev(True, dq.data_ptr(), nq, k, outs[2].data_ptr(), max_radius=1)
     torch.cuda.synchronize()
-    streams = [torch.cuda.Stream() for _ in range(G)]
-    outs = [[torch.empty((nq, k), dtype=torch.int64, device="cuda") for _ in range(3)] for _ in range(G)]
-    errors = []
+    ret[rank] = ([o.cpu().numpy().view(np.uint64).copy() for o in outs], n_x)
+    for c in conns:                                     # nobody closes its window while a peer may still store into it
+        c.send("done")
+    for c in conns:
+        c.recv()
+    ix.close()
 
-    def run(g):
-        try:
-            with torch.cuda.stream(streams[g]):
-                s = streams[g].cuda_stream
-                ixs[g].search_sharded_dev(True, dq.data_ptr(), nq, k, outs[g][0].data_ptr(), stream=s)
-                assert ixs[g].get_param("xchg.last") >= 3       # bootstrap + one per step + the result rows
-                ixs[g].search_sharded_dev(False, dq.data_ptr(), nq, k, outs[g][1].data_ptr(), stream=s)
-                ixs[g].search_sharded_dev(True, dq.data_ptr(), nq, k, outs[g][2].data_ptr(), max_radius=1, stream=s)
-                streams[g].synchronize()
-        except Exception as ex:
-            errors.append(ex)
 
-    threads = [threading.Thread(target=run, args=(g,)) for g in range(G)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    assert not errors, errors
+def test_two_shards_over_peer_windows(oracle):
+    """The peer-memory exchange (verticut_b200/csrc/xchg.cuh) between two shards that live in two PROCESSES sharing one GPU: each
+    rank opens the other's window through its CUDA IPC handle (vc_xchg_open) - the mechanism of the multi-GPU path, minus
+    NVLink -; the settle kernel's histogram rows and the finish kernel's top-k rows go through the windows, and
+    vc_search_sharded_dev returns the merged answer on both ranks.  Merged result == oracle, exactly, for the MIH search, the
+    linear scan and a fixed-radius search.  (Two contexts on one GPU are time-sliced, so a rank's wait kernel spins through its
+    slice until the peer's slice has produced - slow, which is fine here; tests/test_gpu_nccl.py is the same over two GPUs.)"""
+    import multiprocessing as mp
+    n, nq, k, G = 1_200_000, 48, 100, 2
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    ctx = mp.get_context("spawn")
+    a, b = ctx.Pipe()
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_peer_rank, args=(0, G, n, nq, k, [a], ret)), ctx.Process(target=_peer_rank, args=(1, G, n, nq, k, [b], ret))]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    for p in procs:
+        if p.is_alive():
+            p.terminate()
+        assert p.exitcode == 0, "rank process failed (exit code %s)" % p.exitcode
     want = oracle.scan_synth(12345, 0, 1, n, 8, queries, k, n_procs=4)
     want_r1 = oracle.scan_synth(12345, 0, 1, n, 8, queries, k, m=4, max_radius=1, n_procs=4)
     for g in range(G):
-        np.testing.assert_array_equal(outs[g][0].cpu().numpy().view(np.uint64), want)
-        np.testing.assert_array_equal(outs[g][1].cpu().numpy().view(np.uint64), want)
-        np.testing.assert_array_equal(outs[g][2].cpu().numpy().view(np.uint64), want_r1)
-        ixs[g].close()
+        outs, n_x = ret[g]
+        assert n_x >= 3                                  # bootstrap + one per step + the result rows
+        np.testing.assert_array_equal(outs[0], want)
+        np.testing.assert_array_equal(outs[1], want)
+        np.testing.assert_array_equal(outs[2], want_r1)

@@ -127,8 +127,9 @@ struct vc_index {
   uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
   int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(16384, 16 k))
   // a step that probes radius 0 together with radius 1 verifies the queries' own (radius-0) buckets first, on the exact distance, and
-  // the other buckets after them with the lower-bound filter: -1 = when the step has >= 2 queries per probed bucket, 0 never, 1 always
-  int64_t mih_r0_first = -1;
+  // the other buckets after them with the lower-bound filter: -1 = when the step has >= 2 queries per probed bucket, 0 never, 1 always.
+  // Measured slower than one launch on the exact distance (batch 16384: 10.6 vs 9.9 ms; profiles/ab_r02.md): off.
+  int64_t mih_r0_first = 0;
   int64_t mih_split_r0 = 0;       // 1: radius 0 is a search step of its own (tighter thresholds for radius 1) instead of being probed together with radius 1
   int64_t mih_cap = 0;            // candidate-buffer entries per query (0: bmih_cap_for(k)); small values force the overflow path in tests
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
