@@ -158,6 +158,12 @@ struct vc_index {
   bool x_pushed = false;          // ... and says here whether it did
   XchgDev x_finish;               // ... into this exchange
   int64_t x_enabled = 1;          // knob "xchg": 0 = keep the all-reduce hook / NCCL for everything
+  // knob "xchg.allreduce": the histogram sums over peer memory?  1 always, 0 never (hook), -1 = only while a rank's payload times the
+  // number of peers stays below 2 MB.  Every rank stores its whole payload into every window (G - 1 times the payload out of each
+  // GPU), where the NVSwitch reduces an NCCL all-reduce in the fabric: measured at 8 GPUs, 6.3 MB per rank, 0.10 ms per exchange
+  // slower than ncclAllReduce (profiles/scale_r02.json); the result rows (an all-gather, no reduction to be had) always go over
+  // peer memory.
+  int64_t x_allreduce = -1;
   int64_t last_xchg = 0;          // exchanges of the last search that went over peer memory
   bool sharded() const { return allreduce_fn != nullptr || x_open; }
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
@@ -1054,8 +1060,13 @@ static uint32_t xchg_push_grid(const vc_index* ix, uint64_t bytes) {
 }
 // Sum of the n_words u32 at d_words over all shards, in place: over peer memory when the windows are open and the payload
 // fits a slot, else through the caller's all-reduce hook (NCCL).  Every shard makes the same choice (same sizes everywhere).
+static bool xchg_allreduce_wanted(const vc_index* ix, uint64_t bytes) {
+  if (!xchg_fits(ix, bytes)) return false;
+  if (!ix->allreduce_fn) return true;                       // no hook: peer memory is the only way
+  return ix->x_allreduce > 0 || (ix->x_allreduce < 0 && bytes * (ix->x_world - 1) <= (2ull << 20));
+}
 static int shard_allreduce(vc_index* ix, uint32_t* d_words, uint64_t n_words, cudaStream_t st) {
-  if (xchg_fits(ix, n_words * 4)) {
+  if (xchg_allreduce_wanted(ix, n_words * 4)) {
     const uint32_t grid = xchg_push_grid(ix, n_words * 4);
     const XchgDev x = xchg_begin(ix, n_words * 4, grid);
     xchg_push(ix, x, d_words, n_words * 4, grid, st);
@@ -1305,7 +1316,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     // id-sharded search: the histograms are summed over the shards, so that every GPU filters and stops on the k-th
     // distance of the WHOLE database (and all ranks walk through the same steps).  Over peer memory the settle kernel
     // itself stores its rows into every shard's window and xchg_sum_kernel adds the G slots up; else the hook (NCCL).
-    if (ix->sharded() && xchg_fits(ix, (uint64_t)nq * Cfg::HB * 4)) {
+    if (ix->sharded() && xchg_allreduce_wanted(ix, (uint64_t)nq * Cfg::HB * 4)) {
       const XchgDev x = xchg_begin(ix, (uint64_t)nq * Cfg::HB * 4, n_active);
       bmih_settle_kernel<W><<<n_active, 256, 0, st>>>(p, cur, n_active, xhist, x);
       xchg_sum_kernel<<<xchg_push_grid(ix, (uint64_t)nq * Cfg::HB * 4), 256, 0, st>>>(x, xhist, (uint64_t)nq * Cfg::HB);
@@ -1613,6 +1624,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.tc_ratio")) ix->mih_tc_ratio = value;
   else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
   else if (!strcmp(name, "xchg")) ix->x_enabled = value;
+  else if (!strcmp(name, "xchg.allreduce")) ix->x_allreduce = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
   else if (!strcmp(name, "mih.split_r0")) ix->mih_split_r0 = value;
   else if (!strcmp(name, "mih.r0_first")) ix->mih_r0_first = value;

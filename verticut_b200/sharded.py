@@ -137,7 +137,8 @@ class ShardedSearcher:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         self.peer_windows = bool(int(flag.item()))
         if self.peer_windows:
-            self.exchange = "stores into the peers' memory over NVLink (xchg.cuh), NCCL only for payloads above %d MB" % (self.XCHG_SLOT_BYTES >> 20)
+            self.exchange = ("result rows: stores into the peers' memory over NVLink (xchg.cuh); histogram sums: the same while payload x peers "
+                             "<= 2 MB, else " + self.exchange)
         else:
             self.index.set_param("xchg", 0)
         dist.barrier(group=self.group)
@@ -186,9 +187,6 @@ class ShardedSearcher:
         nq = d_queries.shape[0]
         stream = self._stream(d_queries.device)
         if mode == "mih":
-            if self.world > 1 and self.exchange != "none":
-                # the shards' bootstrap samples are summed (bmih_boot_tau_kernel): G shards need 1 / G of the sample each
-                self.index.set_param("mih.boot_sample", max(2048, max(16384, 16 * k) // self.world))
             self.index.search_mih_dev(d_queries.data_ptr(), nq, k, out_keys.data_ptr(), approximate=approximate,
                                       max_radius=max_radius, stream=stream)
         elif mode == "linear":
@@ -209,8 +207,6 @@ class ShardedSearcher:
         local, gathered, merged = self._buffers(nq, k, d_queries.device)
         if self.peer_windows and nq * k * 8 <= self.XCHG_SLOT_BYTES and mode in ("mih", "linear"):
             # search + exchange + merge in one call, the exchange being the search kernels' own stores into the peers' windows
-            if mode == "mih":
-                self.index.set_param("mih.boot_sample", max(2048, max(16384, 16 * k) // self.world))
             self.index.search_sharded_dev(mode == "mih", d_queries.data_ptr(), nq, k, merged.data_ptr(), approximate=approximate,
                                           max_radius=max_radius, stream=self._stream(d_queries.device))
             return merged
