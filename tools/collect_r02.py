@@ -61,8 +61,11 @@ def main():
 
     rows = []
     for n, peer, nccl in ((1, "r02_bench_final.json", None), (2, "r02_bench2_peer.json", "r02_bench2_nccl.json"),
-                          (4, "r02_bench4_peer.json", "r02_bench4_nccl.json"), (8, "r02_bench8_peer.json", "r02_bench8_nccl.json")):
-        for kind, name in (("peer-memory exchange" if n > 1 else "single GPU", peer), ("NCCL (VC_XCHG=0)", nccl)):
+                          (8, "r02_bench8_peer.json", "r02_bench8_nccl.json"), (8, "r02_bench8_hybrid.json", "r02_bench8_nccl2.json"),
+                          (8, "r02_bench8_q4096.json", None)):
+        for kind, name in ((("peer-memory exchange for everything (2 K bootstrap sample per shard)" if "peer" in (peer or "") else
+                             "results over peer memory, histogram sums over NCCL (16 K bootstrap sample per shard)") if n > 1 else "single GPU", peer),
+                           ("NCCL only (VC_XCHG=0)" + (" (2 K bootstrap sample per shard)" if nccl and "nccl2" not in nccl else ""), nccl)):
             d = load(name) if name else None
             if d is None:
                 continue

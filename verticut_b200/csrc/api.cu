@@ -797,7 +797,12 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   uint32_t* xhist = (uint32_t*)(sb + o_xhist);
   p.qlist = ident;
   // >= scan.tc_min queries per code: the distance filter goes to the tensor cores (tcverify.cuh)
-  const bool use_tc = ix->scan_tc > 0 || (ix->scan_tc < 0 && W == 1 && nq >= (uint32_t)ix->scan_tc_min && k <= 128);
+  // by size: 64-bit codes, >= scan.tc_min queries AND a shard of >= 2^29 codes.  The tensor-core kernel flags a ROW (one code against
+  // all queries of the item) when any of them passes the largest threshold of the item, and takes the exact path for the whole
+  // row: while the thresholds are still settling - the first tens of millions of codes of a scan, whatever its length - that is
+  // far more expensive than the POPC kernel's per-pair hit path.  Measured: 1.13 - 1.16 x the POPC kernel on 1 B codes, 0.5 x on a
+  // 125 M-code shard (profiles/tc_r02.md).
+  const bool use_tc = ix->scan_tc > 0 || (ix->scan_tc < 0 && W == 1 && nq >= (uint32_t)ix->scan_tc_min && k <= 128 && ix->n >= (1ull << 29));
   const bool tc_v1 = ix->scan_tc == 2 || ix->scan_tc < 0;       // by size: the version that measured faster than the POPC kernel
   p.cpi = use_tc ? kTcCpi : 8 * Cfg::STEP;
   p.qt = use_tc ? (tc_v1 ? (nq > 64 ? tc1_max_qt<W>() : 64u) : tc_max_qt<W>()) : (uint32_t)kBmihQT;

@@ -111,6 +111,7 @@ class ShardedSearcher:
         self._nccl = (nccl, comm)                          # keep the library handle and the communicator alive
         self.index.set_allreduce_nccl(C.cast(nccl.ncclAllReduce, C.c_void_p).value, comm.value)
 
+    XCHG_RESULT_EGRESS = 8 << 20    # result rows go over peer memory while payload x peers stays below this
     XCHG_SLOT_BYTES = 32 << 20      # largest payload of one rank in one exchange that goes over peer memory (else: NCCL)
 
     def _open_peer_windows(self):
@@ -137,8 +138,8 @@ class ShardedSearcher:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
         self.peer_windows = bool(int(flag.item()))
         if self.peer_windows:
-            self.exchange = ("result rows: stores into the peers' memory over NVLink (xchg.cuh); histogram sums: the same while payload x peers "
-                             "<= 2 MB, else " + self.exchange)
+            self.exchange = ("stores into the peers' memory over NVLink (xchg.cuh) while payload x peers <= 8 MB (result rows) / 2 MB "
+                             "(histogram sums), else " + self.exchange + " and all_gather_into_tensor + merge kernel")
         else:
             self.index.set_param("xchg", 0)
         dist.barrier(group=self.group)
@@ -205,7 +206,13 @@ class ShardedSearcher:
         packed words (bit pattern of uint64, ascending), identical on every rank."""
         nq = d_queries.shape[0]
         local, gathered, merged = self._buffers(nq, k, d_queries.device)
-        if self.peer_windows and nq * k * 8 <= self.XCHG_SLOT_BYTES and mode in ("mih", "linear"):
+        # Results over peer memory while the egress (payload x peers) is small - the latency-bound regime; large result sets go
+        # through NCCL, whose all-gather is replicated inside the NVSwitch (measured at 8 GPUs, 13 MB per rank: 0.12 ms per
+        # batch faster than the stores; level at 2 GPUs; profiles/scale_r02.json).  VC_XCHG_RESULTS=1 / 0 force.
+        peer_results = os.environ.get("VC_XCHG_RESULTS", "")
+        small = nq * k * 8 * (self.world - 1) <= self.XCHG_RESULT_EGRESS
+        if (self.peer_windows and nq * k * 8 <= self.XCHG_SLOT_BYTES and mode in ("mih", "linear")
+                and (peer_results == "1" or (peer_results != "0" and small))):
             # search + exchange + merge in one call, the exchange being the search kernels' own stores into the peers' windows
             self.index.search_sharded_dev(mode == "mih", d_queries.data_ptr(), nq, k, merged.data_ptr(), approximate=approximate,
                                           max_radius=max_radius, stream=self._stream(d_queries.device))
