@@ -1,7 +1,9 @@
 """One search workload on one GPU, timed per kernel - for A/B runs (tools/ab.sh) and ncu captures.
-    python tools/probe.py <mih|linear> <n_codes> <batch> [bits=64] [m=4] [k=100] [r=-1] [reps=3] [check=0] [param=value ...]
+    python tools/probe.py <mih|linear> <n_codes> <batch> [bits=64] [m=4] [k=100] [r=-1] [approx=0] [reps=3] [check=0] [shards=1] [param=value ...]
 r >= 0: fixed-radius search (config C5).  check=Q: the first Q queries are also answered by the brute-force scan of the same
-index and must agree bit for bit (exact mode only).  Unknown name=value pairs are index parameters (vc_index_set_param)."""
+index and must agree bit for bit (exact mode only).  shards=G: the index behaves like ONE of G id-shards of a G times larger
+database - the per-step histogram exchange is replaced by "multiply by G" (statistically what the sum over G shards of uniform codes
+gives), so the per-shard kernels of an 8-GPU run can be timed and profiled on one GPU; answers are not meaningful then.  Unknown name=value pairs are index parameters (vc_index_set_param)."""
 import os
 import sys
 import time
@@ -11,7 +13,7 @@ import numpy as np
 from verticut_b200 import capi
 
 mode, n, B = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-opt = {"bits": 64, "m": 4, "k": 100, "r": -1, "reps": 3, "check": 0}
+opt = {"bits": 64, "m": 4, "k": 100, "r": -1, "approx": 0, "reps": 3, "check": 0, "shards": 1}
 knobs = []
 for a in sys.argv[4:]:
     name, v = a.split("=")
@@ -26,12 +28,25 @@ ix.build()
 ix.set_param("profile", 1)
 for name, v in knobs:
     ix.set_param(name, v)
+if opt["shards"] > 1:
+    import torch
+    _views = {}
+
+    def times_g(ptr, n_words, stream):
+        view = _views.get((ptr, n_words))
+        if view is None:
+            class _Raw:
+                __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+            view = _views[(ptr, n_words)] = torch.as_tensor(_Raw(), device="cuda:0")
+        with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0))):
+            view.mul_(opt["shards"])
+    ix.set_allreduce(times_g)
 q = np.random.default_rng(1).integers(0, 256, size=(B, bits // 8), dtype=np.uint8)
 
 
 def once(stats=False):
     if mode == "mih":
-        return ix.search_mih(q, k, max_radius=r, with_stats=stats)
+        return ix.search_mih(q, k, approximate=bool(opt["approx"]), max_radius=r, with_stats=stats)
     return ix.search_linear(q, k)
 
 
@@ -43,7 +58,7 @@ for _ in range(opt["reps"]):
     once()
 dt = (time.perf_counter() - t0) / opt["reps"]
 ns = ix.get_param("last_kernel_ns")
-out = {"mode": mode, "n": n, "B": B, "bits": bits, "m": m, "k": k, "r": r, "kernel_ms": round(ns / 1e6, 3), "e2e_ms": round(dt * 1e3, 3),
+out = {"mode": mode, "n": n, "B": B, "bits": bits, "m": m, "k": k, "r": r, "approx": opt["approx"], "shards": opt["shards"], "kernel_ms": round(ns / 1e6, 3), "e2e_ms": round(dt * 1e3, 3),
        "qps_e2e": round(B / dt, 1)}
 if mode == "mih":
     st = res[3]

@@ -1400,6 +1400,7 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     ix->launches++;
     ix->last_mih_redo = n_redo;
     if (n_redo && (rc = mih_per_query(ix, d_queries, n_redo, k, 0, max_radius, d_out_keys, d_stats, st, rl))) return rc;
+    if (ix->profile) ix->lev_used = std::min(levels, 34);   // the per-query kernel reset it: the step timings stay those of the batched steps
   }
   CU(cudaGetLastError());
   unsigned long long h_bc = 0, tcs[3] = {0, 0, 0};
