@@ -2,8 +2,8 @@
     python tools/probe.py <mih|linear> <n_codes> <batch> [bits=64] [m=4] [k=100] [r=-1] [approx=0] [reps=3] [check=0] [shards=1] [param=value ...]
 r >= 0: fixed-radius search (config C5).  check=Q: the first Q queries are also answered by the brute-force scan of the same
 index and must agree bit for bit (exact mode only).  shards=G: the index behaves like ONE of G id-shards of a G times larger
-database - the per-step histogram exchange is replaced by "multiply by G" (statistically what the sum over G shards of uniform codes
-gives), so the per-shard kernels of an 8-GPU run can be timed and profiled on one GPU; answers are not meaningful then.  Unknown name=value pairs are index parameters (vc_index_set_param)."""
+database - every cross-shard sum is replaced by "times G" (index parameter xchg.emulate; statistically what G shards of uniform codes
+give), so the per-shard kernels of an 8-GPU run can be timed and profiled on one GPU; answers are not meaningful then.  Unknown name=value pairs are index parameters (vc_index_set_param)."""
 import os
 import sys
 import time
@@ -23,24 +23,15 @@ for a in sys.argv[4:]:
         knobs.append((name, int(v)))
 bits, m, k, r = opt["bits"], opt["m"], opt["k"], opt["r"]
 ix = capi.Index(bits, m if mode == "mih" else 0)
+if opt["shards"] > 1:
+    ix.set_param("id_stride", opt["shards"])     # ids dealt round-robin over the shards, as bench.py --gpus G does
 ix.add_synthetic(n, 12345)
 ix.build()
 ix.set_param("profile", 1)
 for name, v in knobs:
     ix.set_param(name, v)
 if opt["shards"] > 1:
-    import torch
-    _views = {}
-
-    def times_g(ptr, n_words, stream):
-        view = _views.get((ptr, n_words))
-        if view is None:
-            class _Raw:
-                __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
-            view = _views[(ptr, n_words)] = torch.as_tensor(_Raw(), device="cuda:0")
-        with torch.cuda.stream(torch.cuda.ExternalStream(int(stream or 0))):
-            view.mul_(opt["shards"])
-    ix.set_allreduce(times_g)
+    ix.set_param("xchg.emulate", opt["shards"])
 q = np.random.default_rng(1).integers(0, 256, size=(B, bits // 8), dtype=np.uint8)
 
 

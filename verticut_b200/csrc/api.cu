@@ -164,8 +164,12 @@ struct vc_index {
   // slower than ncclAllReduce (profiles/scale_r02.json); the result rows (an all-gather, no reduction to be had) always go over
   // peer memory.
   int64_t x_allreduce = -1;
+  // knob "xchg.emulate" = G > 1 (measurements only, tools/probe.py shards=G): this index behaves like ONE of G id-shards of a
+  // G times larger database - every cross-shard sum is replaced by "times G", statistically what G shards of uniform codes give -
+  // so that the per-shard kernels of a multi-GPU search can be timed and profiled on one GPU.  The answers are not those of any database.
+  int64_t x_emulate = 0;
   int64_t last_xchg = 0;          // exchanges of the last search that went over peer memory
-  bool sharded() const { return allreduce_fn != nullptr || x_open; }
+  bool sharded() const { return allreduce_fn != nullptr || x_open || x_emulate > 1; }
   int64_t mih_table_steps = -1;   // stop rule tested after every table of a radius: 0 never (reference-like radius steps), 1 always, -1 auto    // batched path when the average bucket holds at least this many codes
   int64_t last_mih_batched = 0, last_mih_levels = 0, last_mih_items = 0, last_mih_bucket_codes = 0, last_mih_redo = 0;
   // optional device-side timing of the dominant kernel of the last search ("profile" = 1)
@@ -1070,7 +1074,16 @@ static bool xchg_allreduce_wanted(const vc_index* ix, uint64_t bytes) {
   if (!ix->allreduce_fn) return true;                       // no hook: peer memory is the only way
   return ix->x_allreduce > 0 || (ix->x_allreduce < 0 && bytes * (ix->x_world - 1) <= (2ull << 20));
 }
+__global__ void emulate_sum_kernel(uint32_t* w, uint64_t n, uint32_t g) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] *= g;
+}
 static int shard_allreduce(vc_index* ix, uint32_t* d_words, uint64_t n_words, cudaStream_t st) {
+  if (ix->x_emulate > 1) {
+    emulate_sum_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, st>>>(d_words, n_words, (uint32_t)ix->x_emulate);
+    ix->launches++;
+    return VC_OK;
+  }
   if (xchg_allreduce_wanted(ix, n_words * 4)) {
     const uint32_t grid = xchg_push_grid(ix, n_words * 4);
     const XchgDev x = xchg_begin(ix, n_words * 4, grid);
@@ -1631,6 +1644,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "mih.global_key")) ix->mih_global_key = value;
   else if (!strcmp(name, "xchg")) ix->x_enabled = value;
   else if (!strcmp(name, "xchg.allreduce")) ix->x_allreduce = value;
+  else if (!strcmp(name, "xchg.emulate")) ix->x_emulate = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
   else if (!strcmp(name, "mih.split_r0")) ix->mih_split_r0 = value;
   else if (!strcmp(name, "mih.r0_first")) ix->mih_r0_first = value;
