@@ -179,3 +179,53 @@ def test_batched_first_step_variants_are_exact(oracle, knobs, n, bits, m, nq, k)
         base._check_exact(oracle, n, bits, m, nq, k)
     finally:
         base.EXTRA_PARAMS = {}
+
+
+@pytest.mark.parametrize("bits,m,k,how", [
+    (64, 8, 3, "longest bucket alone holds 20 k candidates: nothing is counted"),
+    (64, 8, 10, "sum of the buckets decides only after counting"),
+    (64, 8, 62, "20 k = 1240 ~ the distinct candidates of radius 0: about half of the queries go on to radius 1"),
+    (128, 16, 5, "128-bit codes"),
+    (64, 4, 10, "short buckets: every query is answered by the per-query kernel"),
+])
+def test_batched_approximate(oracle, bits, m, k, how):
+    """Approximate mode (search_worker.cc:93-157) through the batched path: radius 0 batched, the queries that need more one by
+    one; ids, distances, stop radius and the distinct-candidate count equal the oracle's."""
+    n, nq = 40_000, 48
+    codes, ix = base._mk(oracle, n, bits, m)
+    queries = oracle.synth_codes(67890, 0, nq, bits // 8)
+    oix = oracle.Index(codes, m)
+    oid, od, oc, ost = oix.search(queries, k, approximate=True)
+    for with_stats in (True, False):
+        ids, dists, counts, stats = ix.search_mih(queries, k, approximate=True, with_stats=with_stats)
+        assert ix.get_param("mih.last_batched") == 1
+        np.testing.assert_array_equal(ids, oid)
+        np.testing.assert_array_equal(dists, od)
+        np.testing.assert_array_equal(counts, oc)
+        if with_stats:
+            np.testing.assert_array_equal(stats["radius"], [s["radius"] for s in ost])
+            np.testing.assert_array_equal(stats["unique"], [s["unique"] for s in ost])
+    n_beyond_radius0 = sum(1 for s in ost if s["radius"] > 0)
+    assert ix.get_param("mih.last_redo") == n_beyond_radius0
+    if "half" in how:
+        assert 0 < n_beyond_radius0 < nq
+    ix.close()
+
+
+def test_batched_approximate_equals_per_query_kernel_on_long_buckets(oracle):
+    n, nq, k = 3_000_000, 200, 20
+    ix = capi.Index(64, 8)                   # m = 8: 256 buckets of ~11 700 codes per table - radius 0 is enough for every query
+    ix.add_synthetic(n, 777)
+    ix.build()
+    queries = oracle.synth_codes(4242, 0, nq, 8)
+    ix.set_param("mih.batched", 0)
+    a = ix.search_mih(queries, k, approximate=True)
+    assert ix.get_param("mih.last_batched") == 0
+    ix.set_param("mih.batched", -1)
+    b = ix.search_mih(queries, k, approximate=True)
+    assert ix.get_param("mih.last_batched") == 1 and ix.get_param("mih.last_redo") == 0
+    for x, y in zip(a[:3], b[:3]):
+        np.testing.assert_array_equal(x, y)
+    for f in ("radius", "n_results", "probes", "candidates", "unique"):
+        np.testing.assert_array_equal(a[3][f], b[3][f])
+    ix.close()

@@ -105,7 +105,7 @@ struct vc_index {
   size_t smem_optin = 0;
   // scratch
   DevBuf d_q, d_partial, d_partial2, d_keys, d_ids, d_dists, d_counts, d_stats, d_small, d_gstate;
-  DevBuf b_state, b_buckets, b_qlist, b_items, b_redo, b_idh;   // batched MIH
+  DevBuf b_state, b_buckets, b_qlist, b_items, b_redo, b_idh, b_approx;   // batched MIH
   PinBuf h_q, h_ids, h_dists, h_counts, h_stats, h_small;
   // knobs
   int64_t scan_prefilter = -1;    // -1 auto, 0 off, 1 on
@@ -268,7 +268,7 @@ void vc_index_destroy(vc_index* ix) {
   for (cudaEvent_t e : ix->lev_x) if (e) cudaEventDestroy(e);
   if (ix->ev_s0) { cudaEventDestroy(ix->ev_s0); cudaEventDestroy(ix->ev_s1); }
   DevBuf* db[] = {&ix->d_q, &ix->d_partial, &ix->d_partial2, &ix->d_keys, &ix->d_ids, &ix->d_dists, &ix->d_counts, &ix->d_stats, &ix->d_small, &ix->d_gstate,
-                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_redo, &ix->b_idh, &ix->b_trace};
+                   &ix->b_state, &ix->b_buckets, &ix->b_qlist, &ix->b_items, &ix->b_redo, &ix->b_idh, &ix->b_approx, &ix->b_trace};
   for (DevBuf* b : db) b->release();
   PinBuf* pb[] = {&ix->h_q, &ix->h_ids, &ix->h_dists, &ix->h_counts, &ix->h_stats, &ix->h_small};
   for (PinBuf* b : pb) b->release();
@@ -1425,6 +1425,40 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   return VC_OK;
 }
 
+// Approximate mode (search_worker.cc:93-157) where buckets are long: the fixed-radius-0 search of the batched path answers every
+// query that knows k * 20 distinct candidates after radius 0 (approx_radius0_kernel decides which, bmih.cuh); the others - none on
+// a large uniform index - are answered by the per-query kernel, which widens the radius as the reference does.
+template <int W>
+static int mih_approx_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, uint64_t* d_out_keys, vc_query_stats* d_stats,
+                              cudaStream_t st) {
+  int rc;
+  const size_t o_unique = 0, o_flag = (size_t)nq * 8, o_list = o_flag + (size_t)nq * 4, o_n = o_list + (size_t)nq * 4;
+  if ((rc = ix->b_approx.ensure(o_n + 256))) return rc;
+  unsigned char* base = (unsigned char*)ix->b_approx.p;
+  unsigned long long* unique0 = (unsigned long long*)(base + o_unique);
+  uint32_t* flag = (uint32_t*)(base + o_flag);
+  uint32_t* list = (uint32_t*)(base + o_list);
+  uint32_t* n_list = (uint32_t*)(base + o_n);
+  approx_radius0_kernel<W><<<nq, 256, 0, st>>>((const uint32_t*)d_queries, ix->d_tab, ix->m, ix->sbits, nq,
+                                               (unsigned long long)k * VC_APPROXIMATE_FACTOR, d_stats != nullptr ? 1 : 0, unique0, flag);
+  ix->launches++;
+  if ((rc = mih_batched<W>(ix, d_queries, nq, k, 0, d_out_keys, d_stats, st))) return rc;
+  if (d_stats) { approx_stats_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_stats, unique0, flag, nq); ix->launches++; }
+  CU(cudaMemsetAsync(n_list, 0, 4, st));
+  bmih_redo_list_kernel<<<(nq + 255) / 256, 256, 0, st>>>(flag, nq, list, n_list);
+  ix->launches++;
+  uint32_t n_redo = 0;
+  CU(cudaMemcpyAsync(&n_redo, n_list, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const int64_t tie_redo = ix->last_mih_redo;
+  const int lev = ix->lev_used;
+  if (n_redo && (rc = mih_per_query(ix, d_queries, n_redo, k, 1, -1, d_out_keys, d_stats, st, list))) return rc;
+  ix->last_mih_redo = tie_redo + n_redo;
+  if (ix->profile) ix->lev_used = lev;
+  CU(cudaGetLastError());
+  return VC_OK;
+}
+
 extern "C" {
 
 int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
@@ -1447,6 +1481,15 @@ int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t
     if (ix->W == 1) return mih_batched<1>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
     if (ix->W == 2) return mih_batched<2>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
     return mih_batched<4>(ix, d_queries, nq, k, max_radius, d_out_keys, d_stats, st);
+  }
+  // approximate mode: batched while the queries' own buckets alone hold (twice) the k * 20 distinct candidates the mode stops at
+  const bool approx_batched = approximate != 0 && max_radius < 0 && ix->sbits <= 16 && k < (uint32_t)kBmihSort / 2 && !ix->sharded() &&
+                              (ix->mih_batched > 0 || (ix->mih_batched < 0 && (ix->n >> ix->sbits) * ix->m >= 2ull * k * VC_APPROXIMATE_FACTOR &&
+                                                       (ix->n >> ix->sbits) >= (uint64_t)ix->mih_min_bucket));
+  if (approx_batched) {
+    if (ix->W == 1) return mih_approx_batched<1>(ix, d_queries, nq, k, d_out_keys, d_stats, st);
+    if (ix->W == 2) return mih_approx_batched<2>(ix, d_queries, nq, k, d_out_keys, d_stats, st);
+    return mih_approx_batched<4>(ix, d_queries, nq, k, d_out_keys, d_stats, st);
   }
   return mih_per_query(ix, d_queries, nq, k, approximate, max_radius, d_out_keys, d_stats, st);
 }

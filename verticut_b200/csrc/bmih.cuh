@@ -1022,6 +1022,71 @@ __global__ void bmih_finish_kernel(const BmihParams p, uint64_t* out_keys, vc_qu
 }
 
 // queries whose candidate buffer overflowed: listed for the per-query kernel, which writes their rows of the output itself
+// ---- approximate mode on the batched path (api.cu: mih_approx_batched) ---------------------------------------
+// search_K_approximate_nearest_neighbors (search_worker.cc:93-157) widens the radius until k * 20 DISTINCT candidates are
+// known (knn_found_, :117-124) and returns the k best of them.  With long buckets that is radius 0 for nearly every query:
+// the answer is then the fixed-radius-0 search, which the batched path does, and what remains is to know, per query,
+// whether radius 0 really was enough and - for the statistics - how many distinct candidates it saw.  One CTA per query:
+// the query's m own buckets; a bucket holds distinct codes, so the longest one is a lower bound and the sum an upper bound
+// of the count; only when those do not decide (or the exact count is asked for) are the buckets streamed and the codes
+// counted that no EARLIER table also finds at radius 0 (the first-discoverer rule).
+// flag[q] = 1: radius 0 is not enough, the per-query kernel answers this query.
+template <int W>
+__global__ void __launch_bounds__(256) approx_radius0_kernel(const uint32_t* __restrict__ queries, const TableDev* __restrict__ tables,
+                                                             uint32_t m, uint32_t sbits, uint32_t nq, unsigned long long need,
+                                                             int count_always, unsigned long long* unique0, uint32_t* flag) {
+  __shared__ uint32_t s_start[kMaxTables], s_len[kMaxTables];
+  __shared__ uint32_t s_q[2 * W];
+  __shared__ unsigned long long s_sum;
+  __shared__ uint32_t s_max, s_count;
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  if (q >= nq) return;
+  if (tid < 2 * W) s_q[tid] = queries[(size_t)q * 2 * W + tid];
+  if (tid == 0) { s_sum = 0; s_max = 0; s_count = 0; }
+  __syncthreads();
+  if (tid < m) {
+    uint32_t st = 0, ln = 0;
+    table_lookup(tables[tid], substring<W>(s_q, tid, sbits), st, ln);
+    s_start[tid] = st; s_len[tid] = ln;
+    atomicAdd(&s_sum, (unsigned long long)ln);
+    atomicMax(&s_max, ln);
+  }
+  __syncthreads();
+  if (!count_always) {
+    if ((unsigned long long)s_max >= need) { if (tid == 0) { unique0[q] = ~0ull; flag[q] = 0; } return; }
+    if (s_sum < need) { if (tid == 0) { unique0[q] = s_sum; flag[q] = 1; } return; }
+  }
+  uint32_t qw[2 * W];
+#pragma unroll
+  for (int i = 0; i < 2 * W; ++i) qw[i] = s_q[i];
+  uint32_t mine = 0;
+  for (uint32_t t = 0; t < m; ++t) {
+    const uint64_t* bc = tables[t].codes + (size_t)s_start[t] * W;
+    const uint32_t len = s_len[t];
+    if (t == 0) { if (tid == 0) mine += len; continue; }      // nothing precedes table 0
+    for (uint32_t j = tid; j < len; j += 256) {
+      uint32_t x[2 * W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint64_t c = __ldcs(bc + (size_t)j * W + w);
+        x[2 * w] = (uint32_t)c ^ qw[2 * w]; x[2 * w + 1] = (uint32_t)(c >> 32) ^ qw[2 * w + 1];
+      }
+      bool first = true;
+      for (uint32_t t2 = 0; t2 < t; ++t2) first = first && substring<W>(x, t2, sbits) != 0;
+      mine += first ? 1u : 0u;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((tid & 31) == 0 && mine) atomicAdd(&s_count, mine);
+  __syncthreads();
+  if (tid == 0) { unique0[q] = s_count; flag[q] = (unsigned long long)s_count < need ? 1u : 0u; }
+}
+// statistics of the queries that ended at radius 0: the distinct-candidate count (the batched search wrote the rest)
+__global__ void approx_stats_kernel(vc_query_stats* stats, const unsigned long long* unique0, const uint32_t* flag, uint32_t nq) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq && !flag[q]) stats[q].unique = unique0[q];
+}
+
 __global__ void bmih_redo_list_kernel(const uint32_t* gflag, uint32_t nq, uint32_t* list, uint32_t* n_list) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < nq && (gflag[q] & 1u)) list[atomicAdd(n_list, 1u)] = q;
