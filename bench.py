@@ -452,6 +452,27 @@ def main():
         batch_4096 = {"queries_per_s": 4096 / (ms * 1e-3), "ms_per_batch": ms, "verify_kernel_ms": float(np.mean(ks)) * 1e-6,
                       "what": "the same measurement with round 1's batch of 4096 queries (device-resident), %d batches" % reps}
 
+    # ---- the reference's approximate mode (search_worker.cc:93-157: stop at 20 k distinct candidates) on the same index, one GPU ------
+    approximate_mode = None
+    if args.config == "headline" and mode == "mih" and world == 1:
+        keys_a = torch.empty((Q, K_NN), dtype=torch.int64, device=dev)
+        cur = torch.cuda.current_stream().cuda_stream
+        for i in range(2):
+            ix.search_mih_dev(dev_batches[i % len(dev_batches)].data_ptr(), Q, K_NN, keys_a.data_ptr(), approximate=True, stream=cur)
+        torch.cuda.synchronize()
+        reps = max(3, min(args.steps, 5))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(reps):
+            ix.search_mih_dev(dev_batches[i % len(dev_batches)].data_ptr(), Q, K_NN, keys_a.data_ptr(), approximate=True, stream=cur)
+        s1.record()
+        torch.cuda.synchronize()
+        ms = s0.elapsed_time(s1) / reps
+        approximate_mode = {"queries_per_s": Q / (ms * 1e-3), "ms_per_batch": ms, "batch": Q, "batched": bool(ix.get_param("mih.last_batched")),
+                            "queries_answered_by_the_per_query_kernel": int(ix.get_param("mih.last_redo")),
+                            "what": "vc_search_mih_dev(approximate = 1), device-resident, %d batches; not part of `value`" % reps}
+        del keys_a
+
     value, ms_step, kernel_ns, clocks = headline["value"], headline["ms_step"], headline["kernel_ns"], headline["clocks"]
     launches, radius = headline["launches"], headline["radius"]
 
@@ -626,7 +647,7 @@ def main():
                        "l2": "inputs larger than L2 (index %.1f GB per GPU, >= 300 MB touched per query)" % (ix.info()["device_bytes"] / 1e9),
                        "parallelism": "id-shard x%d (ids interleaved), top-k all-gather + merge kernel, per-step exchange of distance / id histograms: %s" % (world, searcher.exchange)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "integer_pipe": integer_pipe, "cpu_baseline": cpu_baseline,
-            "oracle_check": headline["ocheck"], "breakdown": headline["breakdown"], "batch_4096": batch_4096,
+            "oracle_check": headline["ocheck"], "breakdown": headline["breakdown"], "batch_4096": batch_4096, "approximate_mode": approximate_mode,
             "parity_selfcheck": None if headline["parity_ok"] is None else "mih == linear scan on 8 queries: %s" % headline["parity_ok"],
             "scan": scan, "build": {"generate_s": t_gen, "build_tables_s": t_build, "index_GB": ix.info()["device_bytes"] / 1e9},
         }

@@ -12,6 +12,46 @@ from verticut_b200.sharded import shard_interleaved, shard_range
 pytestmark = pytest.mark.gpu
 
 
+def test_python_hook_on_the_default_stream_equals_the_in_library_emulation():
+    """A Python all-reduce callback that multiplies by G on the library's stream (handle 0 = the legacy default stream) must give
+    exactly what the library's own "times G" (`xchg.emulate`, tools/probe.py shards=G) gives - the work the callback enqueues is
+    ordered with the library's kernels.  (torch.cuda.ExternalStream(0) is not; sharded.py maps handle 0 to torch's default stream.)"""
+    import torch
+    G, n, nq, k = 8, 3_000_000, 512, 100
+    queries = np.random.default_rng(5).integers(0, 256, size=(nq, 8), dtype=np.uint8)
+    res = {}
+    for how in ("library", "python"):
+        ix = capi.Index(64, 4)
+        ix.set_param("id_stride", G)
+        ix.add_synthetic(n, 12345)
+        ix.build()
+        ix.set_param("mih.batched", 1)
+        calls = []
+        if how == "library":
+            ix.set_param("xchg.emulate", G)
+        else:
+            def times_g(ptr, n_words, stream):
+                class _Raw:
+                    __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+                view = torch.as_tensor(_Raw(), device=torch.device("cuda", 0))
+                handle = int(stream or 0)
+                target = torch.cuda.default_stream() if handle == 0 else torch.cuda.ExternalStream(handle)
+                with torch.cuda.stream(target):
+                    view.mul_(G)
+                calls.append(n_words)
+            ix.set_allreduce(times_g)
+        for _ in range(2):
+            res[how] = ix.search_mih(queries, k)
+        res[how + ".levels"] = ix.get_param("mih.last_levels")
+        assert how == "library" or calls
+        ix.close()
+    assert res["library.levels"] == res["python.levels"]
+    for a, b in zip(res["library"][:3], res["python"][:3]):
+        np.testing.assert_array_equal(a, b)
+    for f in ("radius", "probes", "candidates"):
+        np.testing.assert_array_equal(res["library"][3][f], res["python"][3][f])
+
+
 @pytest.mark.parametrize("G", [2, 3, 8])
 @pytest.mark.parametrize("mode", ["linear", "mih"])
 def test_sharded_equals_unsharded(oracle, G, mode):

@@ -164,8 +164,12 @@ class ShardedSearcher:
                 __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
             view = t.as_tensor(_Raw(), device=t.device("cuda", self.index.device))
             self._views[key] = view
-        if view.device.type == "cuda" and int(stream or 0) != t.cuda.current_stream(view.device).cuda_stream:
-            with t.cuda.stream(t.cuda.ExternalStream(int(stream or 0), device=view.device)):
+        handle = int(stream or 0)
+        if view.device.type == "cuda" and handle != t.cuda.current_stream(view.device).cuda_stream:
+            # handle 0 is the legacy default stream = torch's default stream; ExternalStream(0) is NOT ordered with it (measured:
+            # work launched under it overtook the library's kernels on stream 0)
+            target = t.cuda.default_stream(view.device) if handle == 0 else t.cuda.ExternalStream(handle, device=view.device)
+            with t.cuda.stream(target):
                 self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
         else:
             self.dist.all_reduce(view, op=self.dist.ReduceOp.SUM, group=self.group)
