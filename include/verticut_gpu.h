@@ -203,8 +203,11 @@ int vc_search_sharded_dev(vc_index* ix, int mih, const void* d_queries, uint32_t
  *   "id_stride"   id of the j-th code added = first_id + j * id_stride (default 1; G for one of G interleaved shards;
  *                 must be set before codes are added; stored by vc_index_save)
  *   "scan.*", "mih.*"   kernel selection and tuning, e.g. "scan.batched", "scan.prefilter", "mih.batched",
- *                 "mih.table_steps", "mih.global_key"; "scan.tc" / "mih.tc" = 1 route the distance filter through the
- *                 tensor-core kernel (off by default: measured slower)
+ *                 "mih.table_steps", "mih.global_key"; "scan.tc" = -1 (default): 64-bit scans of >= "scan.tc_min" (256) queries
+ *                 over >= 2^29 codes use the tensor-core kernel, 0 never, 1 / 2 force a version; "mih.tc" = 1 routes the MIH
+ *                 distance filter through it (off: measured slower)
+ *   "host.chunk"  vc_search_linear / vc_search_mih pass their queries through the device in batches of this many (32 768)
+ *   "xchg", "xchg.allreduce", "xchg.emulate"   the peer-memory exchange of an id-sharded search
  *   "profile", "last_kernel_ns", "launches", "mih.step_*", "tc.last_*"   read-back of timings and statistics */
 int vc_index_set_param(vc_index* ix, const char* name, int64_t value);
 int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value);

@@ -209,3 +209,22 @@ def test_mih_errors():
     with pytest.raises(capi.VerticutError):
         capi.Index(96, 4)
     ix.close()
+
+
+def test_host_calls_chunk_long_query_arrays(oracle):
+    """vc_search_mih / vc_search_linear take any number of queries and pass them through the device `host.chunk` at a time:
+    same answers and statistics as one batch."""
+    n, nq, k = 60_000, 70, 10
+    codes, ix = _mk(oracle, n, 64, 4)
+    queries = oracle.synth_codes(67890, 0, nq, 8)
+    whole = ix.search_mih(queries, k)
+    whole_lin = ix.search_linear(queries, k)
+    ix.set_param("host.chunk", 32)
+    parts = ix.search_mih(queries, k)
+    parts_lin = ix.search_linear(queries, k)
+    for a, b in zip(whole[:3] + whole_lin, parts[:3] + parts_lin):
+        np.testing.assert_array_equal(a, b)
+    for f in ("radius", "n_results", "probes", "candidates"):
+        np.testing.assert_array_equal(whole[3][f], parts[3][f])
+    np.testing.assert_array_equal(whole[0], whole_lin[0])
+    ix.close()

@@ -124,6 +124,7 @@ struct vc_index {
   int64_t mih_cpi_steps = 0;
   int64_t mih_wide = -1;
   int64_t mih_min_bucket = 64;
+  int64_t host_chunk = 32768;              // knob "host.chunk": queries per device batch of the host-buffer calls
   uint32_t max_bucket_len = 0;    // longest bucket of the dense tables (0: not computed yet for this build)
   int64_t mih_boot_sample = 0;    // codes per query of the threshold bootstrap (0: max(16384, 16 k))
   // a step that probes radius 0 together with radius 1 verifies the queries' own (radius-0) buckets first, on the exact distance, and
@@ -1497,10 +1498,26 @@ int vc_search_mih_dev(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t
 // ------------------------------------------------------------------------------------------------
 // host-buffer search entry points: H2D queries, search, unpack, D2H results
 // ------------------------------------------------------------------------------------------------
+static int search_host_chunk(vc_index* ix, bool mih, const void* queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                             uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, vc_query_stats* stats);
+// Host buffers of any length: the queries go through the device in chunks of `host.chunk` (32 768), so that the per-query
+// workspace (candidate buffers, probe lists) stays bounded whatever the caller passes; one chunk = one batch of the batched paths.
 static int search_host(vc_index* ix, bool mih, const void* queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
                        uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, vc_query_stats* stats) {
   if (!ix || (!queries && nq)) return fail(VC_ERR_ARG, "null argument");
   if (k == 0 || k > VC_MAX_K) return fail(VC_ERR_ARG, "k must be in [1, %u]", VC_MAX_K);
+  const uint32_t chunk = (uint32_t)std::max<int64_t>(1, ix->host_chunk);
+  for (uint32_t off = 0; off < nq; off += chunk) {
+    const uint32_t n = std::min(chunk, nq - off);
+    const int rc = search_host_chunk(ix, mih, (const unsigned char*)queries + (size_t)off * ix->W * 8, n, k, approximate, max_radius,
+                                     out_ids ? out_ids + (size_t)off * k : nullptr, out_dists ? out_dists + (size_t)off * k : nullptr,
+                                     out_counts ? out_counts + off : nullptr, stats ? stats + off : nullptr);
+    if (rc) return rc;
+  }
+  return VC_OK;
+}
+static int search_host_chunk(vc_index* ix, bool mih, const void* queries, uint32_t nq, uint32_t k, int approximate, int max_radius,
+                             uint32_t* out_ids, uint32_t* out_dists, uint32_t* out_counts, vc_query_stats* stats) {
   if (nq == 0) return VC_OK;
   DeviceGuard g(ix->device);
   const size_t qbytes = (size_t)nq * ix->W * 8, rk = (size_t)nq * k;
@@ -1703,6 +1720,7 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   }
   else if (!strcmp(name, "mih.wide")) ix->mih_wide = value;
   else if (!strcmp(name, "mih.min_bucket")) ix->mih_min_bucket = value;
+  else if (!strcmp(name, "host.chunk")) ix->host_chunk = std::max<int64_t>(1, value);
   else if (!strcmp(name, "mih.table_steps")) ix->mih_table_steps = value;
   else if (!strcmp(name, "profile")) {
     DeviceGuard g(ix->device);
