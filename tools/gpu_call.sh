@@ -1,5 +1,6 @@
 #!/bin/bash
 # scratch: the command list of the current gpurun call
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_mih.py tests/test_gpu_sharded.py -m gpu -x -q -k "chunk or python_hook or approximate" > gpurun_out/r02_pytest19.log 2>&1; tail -n 5 gpurun_out/r02_pytest19.log
-for b in 1 2 4 8; do python tools/probe.py linear 125000000 $b reps=20 2>&1 | tail -n 1; done > gpurun_out/r02_lin125.log; cat gpurun_out/r02_lin125.log
+python -m pytest tests -m gpu -q > gpurun_out/r02_pytest20.log 2>&1; tail -n 4 gpurun_out/r02_pytest20.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
+python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; tail -n 2 gpurun_out/r02_bench_final.err; cut -c1-600 gpurun_out/r02_bench_final.json

@@ -1207,7 +1207,6 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   int verify_grid = 0;
   int levels = 0;
   int64_t items_total = 0;
-  bool first_verify = true;
   bool loose_majority = true;           // thresholds straight from the bootstrap
   // steps: (radius r, tables [t0, t1)).  A whole radius per step, or - when most queries are about to stop - one
   // table per step, so that the strict rule d_k <= m*r + t can end the search in the middle of a radius.
@@ -1331,7 +1330,6 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     else rc = pf ? launch_bmih_verify<W, true, kBmihU4>(p, ix->num_sms, st, &verify_grid) : launch_bmih_verify<W, false, kBmihU4>(p, ix->num_sms, st, &verify_grid);
     if (rc) return rc;
     if (timed) cudaEventRecord(ix->lev[2 * levels + 1], st);
-    first_verify = false;
     // id-sharded search: the histograms are summed over the shards, so that every GPU filters and stops on the k-th
     // distance of the WHOLE database (and all ranks walk through the same steps).  Over peer memory the settle kernel
     // itself stores its rows into every shard's window and xchg_sum_kernel adds the G slots up; else the hook (NCCL).
@@ -1389,7 +1387,6 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     }
   }
   if (ix->profile) { ix->lev_used = std::min(levels, 34); ix->ev_valid = true; }
-  (void)first_verify;
   // sharded call over peer memory (vc_search_sharded_dev): unless some query has to be redone below, the finish kernel
   // itself stores the result rows into every shard's window
   ix->x_pushed = false;
