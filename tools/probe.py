@@ -63,6 +63,12 @@ if mode == "mih":
     if batched:
         L = ix.get_param("mih.last_levels")
         out["steps_ms"] = [round(ix.get_param("mih.step_ns.%d" % i) / 1e6, 3) for i in range(L)]
+        try:      # probes + work items in front of each verify launch; settle + exchange + decide behind it; the whole device-side search
+            out["pre_ms"] = [round(ix.get_param("mih.step_pre_ns.%d" % i) / 1e6, 3) for i in range(L)]
+            out["post_ms"] = [round(ix.get_param("mih.step_post_ns.%d" % i) / 1e6, 3) for i in range(L)]
+            out["search_ms"] = round(ix.get_param("mih.search_ns") / 1e6, 3)
+        except capi.VerticutError:
+            pass
         out["step_exec_pairs"] = [ix.get_param("mih.step_exec.%d" % i) for i in range(L)]
         out["step_codes"] = [ix.get_param("mih.step_codes.%d" % i) for i in range(L)]
         ex = float(sum(out["step_exec_pairs"]))

@@ -668,7 +668,9 @@ static uint32_t pow2_at_least(uint32_t v) { uint32_t p = 1; while (p < v) p <<= 
 static int merge_lists(int64_t* launches, const uint64_t* d_lists, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t fanin,
                        uint64_t* d_scratch_a, uint64_t* d_scratch_b, uint64_t* d_out, cudaStream_t st, uint64_t list_stride = 0) {
   if (!list_stride) list_stride = (uint64_t)nq * k;
-  const uint32_t BUF = pow2_at_least(k + kMergeThreads);     // <= 4096 entries = 32 KB: no opt-in needed
+  uint32_t BUF = pow2_at_least(k + kMergeThreads);           // <= 4096 entries = 32 KB: no opt-in needed
+  // a few short lists (the shards' top-k rows): all of them in the buffer at once, one selection pass (topk_compact_block)
+  if ((uint64_t)std::min(n_lists, fanin) * k <= 2048) BUF = std::max(BUF, pow2_at_least(std::min(n_lists, fanin) * k));
   const size_t smem = (size_t)BUF * 8;
   const uint64_t* in = d_lists;
   uint32_t nl = n_lists;

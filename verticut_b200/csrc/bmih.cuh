@@ -36,6 +36,7 @@ namespace vc {
 #endif
 constexpr int kBmihThreads = VC_BMIH_THREADS;
 constexpr int kBmihQT = 32;          // queries per work item
+constexpr int kProbeMasks = 2048;    // probe masks of one table and step the probe kernel keeps in shared memory (C(16, 3) = 560; beyond: unranked per probe)
 constexpr int kBmihSort = 4096;      // entries the settle kernel sorts at a time (shared memory); k must stay below half of it
 constexpr int kBmihCapMin = 4096;    // candidate-buffer entries per query: at least this, see bmih_cap_for
 constexpr int kBmihHitQ = 32 * kBmihQT + 32;   // deferred hits per warp of the verify kernel (bv_hitq): what one warp step can add, plus an undrained rest
@@ -125,9 +126,21 @@ template <int W>
 __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
   uint32_t per_table = 0;                                     // probes per table: all masks of weight r_lo .. radius
   for (uint32_t r = p.r_lo; r <= p.radius; ++r) per_table += c_binom[p.sbits][r];
-  const uint64_t per_q = (uint64_t)per_table * (p.t_end - p.t_begin);
-  const uint64_t total = per_q * p.n_active;
+  const uint32_t per_q = per_table * (p.t_end - p.t_begin);   // the host keeps a step below 2^32 probes: 32-bit divisions below
+  const uint64_t total = (uint64_t)per_q * p.n_active;
   const uint32_t lane = threadIdx.x & 31;
+  // the step's masks, unranked once per CTA: unrank_mask walks the binomial table in constant memory with a different index
+  // in every lane (serialised), and a CTA unranks the same per_table masks for every query it meets
+  __shared__ uint32_t s_mask[kProbeMasks];
+  const bool tabled = per_table <= (uint32_t)kProbeMasks;
+  if (tabled) {
+    for (uint32_t i = threadIdx.x; i < per_table; i += blockDim.x) {
+      uint32_t pidx = i, rad = p.r_lo;
+      while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
+      s_mask[i] = unrank_mask(p.sbits, rad, pidx);
+    }
+    __syncthreads();
+  }
   unsigned long long warp_pairs = 0;                          // lane 0: members of all buckets this warp probed
   // whole warps walk the probe list (the statistics below are aggregated per warp: one atomic per distinct query and
   // warp instead of one per probe - the probes of a query are neighbours, and 11 M atomics on one counter cost 3 ms)
@@ -136,14 +149,20 @@ __global__ void bmih_probe_kernel(const BmihParams p, int pass) {
     const bool valid = it < total;
     uint32_t q = 0xFFFFFFFFu, len = 0, b = 0, key = 0, qkey_of_probe = 1;
     if (valid) {
-      const uint32_t a = (uint32_t)(it / per_q);
-      const uint32_t rem = (uint32_t)(it % per_q);
-      const uint32_t t = p.t_begin + rem / per_table;
-      uint32_t pidx = rem % per_table, rad = p.r_lo;
-      while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
+      const uint32_t a = (uint32_t)it / per_q;
+      const uint32_t rem = (uint32_t)it - a * per_q;
+      const uint32_t tt = rem / per_table;
+      const uint32_t t = p.t_begin + tt;
+      uint32_t pidx = rem - tt * per_table, mask;
+      if (tabled) mask = s_mask[pidx];
+      else {
+        uint32_t rad = p.r_lo;
+        while (pidx >= c_binom[p.sbits][rad]) { pidx -= c_binom[p.sbits][rad]; ++rad; }
+        mask = unrank_mask(p.sbits, rad, pidx);
+      }
       q = p.active[a];
       const uint32_t qkey = substring<W>(p.queries + (size_t)q * 2 * W, t, p.sbits);
-      key = qkey ^ unrank_mask(p.sbits, rad, pidx);
+      key = qkey ^ mask;
       qkey_of_probe = qkey;
       const uint32_t* rp = p.tables[t].row_ptr;
       len = rp[key + 1] - rp[key];
@@ -698,6 +717,8 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   __shared__ uint32_t cnt;
   __shared__ uint64_t s_tau;
   constexpr int HB = BmihCfg<W>::HB;
+  constexpr uint32_t NB = 64 * W + 1;                     // distance bins 0 .. 64 W (HB leaves room for the two scratch words of topk_compact_block)
+  __shared__ uint32_t sh[HB];
   const uint32_t tid = threadIdx.x;
   if (blockIdx.x >= n_list) return;                       // (never true with a peer exchange: the grid is exactly n_list CTAs)
   const uint32_t q = list[blockIdx.x];
@@ -709,7 +730,7 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
     for (uint32_t i = tid; i < n; i += 256) buf[i] = gb[i];
     if (tid == 0) cnt = n;
     __syncthreads();
-    tk = topk_compact(buf, &cnt, kBmihSort, p.k, tid, 256, BlockSync());
+    tk = topk_compact_block(buf, &cnt, kBmihSort, p.k, sh, NB, tid, 256);
   } else {
     // more candidates than fit in shared memory (large k): folded in 256 at a time, the buffer compacted to its k best
     // whenever the next 256 might not fit; entries that no longer beat the running k-th key are dropped on the way in
@@ -717,7 +738,7 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
     __syncthreads();
     for (uint32_t base = 0; base < n; base += 256) {
       if (cnt + 256 > (uint32_t)kBmihSort) {                   // uniform: cnt is stable between barriers
-        const uint64_t t2 = topk_compact(buf, &cnt, kBmihSort, p.k, tid, 256, BlockSync());
+        const uint64_t t2 = topk_compact_block(buf, &cnt, kBmihSort, p.k, sh, NB, tid, 256);
         if (tid == 0) s_tau = t2;
         __syncthreads();
       }
@@ -727,13 +748,13 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
       }
       __syncthreads();
     }
-    tk = topk_compact(buf, &cnt, kBmihSort, p.k, tid, 256, BlockSync());
+    tk = topk_compact_block(buf, &cnt, kBmihSort, p.k, sh, NB, tid, 256);
   }
   const uint32_t kept = cnt;
   for (uint32_t i = tid; i < kept; i += 256) gb[i] = buf[i];
   // per-distance histogram of what is kept -> xhist (for the decide kernel / the cross-shard sum); its prefix
   // sums -> ghist (the cumulative counts the append path maintains)
-  __shared__ uint32_t sh[HB];
+  __syncthreads();
   for (uint32_t i = tid; i < HB; i += 256) sh[i] = 0;
   __syncthreads();
   for (uint32_t i = tid; i < kept; i += 256) atomicAdd(&sh[(uint32_t)(buf[i] >> 32)], 1u);
@@ -751,10 +772,12 @@ __global__ void __launch_bounds__(256) bmih_settle_kernel(const BmihParams p, co
   } else {
     for (uint32_t i = tid; i < HB; i += 256) xhist[(size_t)q * HB + i] = sh[i];
   }
-  if (tid == 0) {
+  if (tid < 32) {                                         // one warp: lane l owns bins [l per, (l + 1) per)
     uint32_t* gc = p.ghist + (size_t)q * HB;
-    uint32_t cum = 0;
-    for (uint32_t d = 0; d <= 64 * W; ++d) { cum += sh[d]; gc[d] = cum; }
+    constexpr uint32_t per = (NB + 31) / 32;
+    uint32_t mine;
+    uint32_t cum = warp_bins_excl(sh, NB, per, tid, mine);
+    for (uint32_t j = 0; j < per; ++j) { const uint32_t d = tid * per + j; if (d < NB) { cum += sh[d]; gc[d] = cum; } }
   }
   if (tid == 0) {
     p.gcnt[q] = kept;

@@ -82,6 +82,70 @@ __device__ __forceinline__ uint64_t topk_compact(uint64_t* buf, uint32_t* cnt, u
 struct WarpSync  { __device__ __forceinline__ void operator()() const { __syncwarp(); } };
 struct BlockSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
+// Exclusive prefix sums of `per` consecutive bins per lane, over one warp: lane l owns bins [l * per, (l + 1) * per).
+// Returns the lane's own sum in `mine` and the sum of all lower lanes' bins as the result.
+__device__ __forceinline__ uint32_t warp_bins_excl(const uint32_t* bins, uint32_t nb, uint32_t per, uint32_t lane, uint32_t& mine) {
+  uint32_t s = 0;
+  for (uint32_t j = 0; j < per; ++j) { const uint32_t b = lane * per + j; if (b < nb) s += bins[b]; }
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += v; }
+  mine = s;
+  return incl - s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// topk_compact for a whole block (nthreads a multiple of 32, all threads call) when the buffer is much longer than k:
+// the bitonic sort costs P log^2 P shared-memory traffic, and most of a long buffer cannot be among the k smallest.  So
+// first a histogram of the distance fields (bin = min(dist, nb - 1)), the first bin b_k at which k entries are reached,
+// and an in-place compaction to the entries of bins <= b_k - k plus the ties of the k-th distance; only those are sorted.
+// Same result as topk_compact (the k smallest, ascending, and the k-th word).  `hist` = nb + 2 words of shared memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t topk_compact_block(uint64_t* buf, uint32_t* cnt, uint32_t cap, uint32_t k,
+                                                       uint32_t* hist, uint32_t nb, uint32_t tid, uint32_t nthreads) {
+  const uint32_t n = min(*cnt, cap);
+  if (n > 256 && n >= 2 * k + 64) {                                   // uniform over the block
+    for (uint32_t i = tid; i < nb + 2; i += nthreads) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += nthreads) {            // one atomic per warp and distinct bin: the entries crowd into 3 - 4 bins
+      const uint32_t i = base + tid;
+      const uint32_t bin = i < n ? min((uint32_t)(buf[i] >> 32), nb - 1) : 0xFFFFFFFFu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      if (i < n && (tid & 31) == (uint32_t)__ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t per = (nb + 31) / 32;
+      uint32_t mine;
+      const uint32_t excl = warp_bins_excl(hist, nb, per, tid, mine);
+      if (excl < k && excl + mine >= k) {                              // exactly one lane: the block holds n >= k entries
+        uint32_t cum = excl, b = tid * per;
+        for (;; ++b) { cum += hist[b]; if (cum >= k) break; }
+        hist[nb] = b;
+      }
+    }
+    __syncthreads();
+    const uint32_t bk = hist[nb];
+    // in place: chunk c reads entries [c T, (c + 1) T) before the barrier and writes after it to slots below the number
+    // kept so far, which is at most (c + 1) T - entries no later chunk still has to read
+    for (uint32_t base = 0; base < n; base += nthreads) {
+      const uint32_t i = base + tid;
+      const uint64_t key = i < n ? buf[i] : kEmptyKey;
+      const bool keep = i < n && min((uint32_t)(key >> 32), nb - 1) <= bk;
+      __syncthreads();
+      const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+      uint32_t wbase = 0;
+      if ((tid & 31) == 0 && mask) wbase = atomicAdd(&hist[nb + 1], (uint32_t)__popc(mask));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (keep) buf[wbase + __popc(mask & ((1u << (tid & 31)) - 1u))] = key;
+    }
+    __syncthreads();
+    if (tid == 0) *cnt = hist[nb + 1];
+    __syncthreads();
+  }
+  return topk_compact(buf, cnt, cap, k, tid, nthreads, BlockSync());
+}
+
 // Hamming distance helpers on 64-bit words held as two 32-bit halves.
 template <int W> struct CodeRegs { uint32_t w[2 * W]; };   // W 64-bit words = 2W 32-bit words
 

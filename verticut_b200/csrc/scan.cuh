@@ -393,6 +393,8 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
   uint64_t* buf = (uint64_t*)smem_raw;            // [BUF]
   __shared__ uint32_t cnt;
   __shared__ uint64_t tau_s;
+  constexpr uint32_t NB = 64 * 4 + 2;             // distance bins 0 .. 256, one more for anything above (topk_compact_block clamps)
+  __shared__ uint32_t mh[NB + 2];
   const uint32_t q = blockIdx.x, grp = blockIdx.y, tid = threadIdx.x;
   const uint32_t l0 = grp * fanin, nl = min(fanin, n_lists - l0);
   if (tid == 0) { cnt = 0; tau_s = kEmptyKey; }
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
   const uint64_t total = (uint64_t)nl * k;
   for (uint64_t base = 0; base < total; base += kMergeThreads) {
     if (cnt + kMergeThreads > BUF) {     // uniform: cnt is stable between barriers
-      uint64_t tau = topk_compact(buf, &cnt, BUF, k, tid, kMergeThreads, BlockSync());
+      uint64_t tau = topk_compact_block(buf, &cnt, BUF, k, mh, NB, tid, kMergeThreads);
       if (tid == 0) tau_s = tau;
       __syncthreads();
     }
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_topk_kernel(const uint64_
     }
     __syncthreads();
   }
-  topk_compact(buf, &cnt, BUF, k, tid, kMergeThreads, BlockSync());
+  topk_compact_block(buf, &cnt, BUF, k, mh, NB, tid, kMergeThreads);
   const uint32_t kept = cnt;
   uint64_t* o = out + ((size_t)grp * nq + q) * k;
   for (uint32_t i = tid; i < k; i += kMergeThreads) o[i] = i < kept ? buf[i] : kEmptyKey;
