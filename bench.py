@@ -26,7 +26,8 @@ oracle_check: a few queries of the batch answered by the CPU oracle over the SAM
   500 M codes (needs >= 4 GPUs; fewer: 62.5 M codes per GPU, flagged), fixed-radius sweep r = 0..3, k = 1000, m = 16
   (VC_BENCH_TABLES=8: the sparse s = 32 tables).
 Environment overrides for quick runs: VC_BENCH_N (total codes), VC_BENCH_Q (batch), VC_BENCH_MODE (mih|linear), VC_BENCH_K,
-VC_BENCH_BITS, VC_BENCH_TABLES, VC_BENCH_ORACLE_Q (queries checked against the oracle; 0 = skip).
+VC_BENCH_BITS, VC_BENCH_TABLES, VC_BENCH_ORACLE_Q (queries checked against the oracle; 0 = skip).  VC_BENCH_WEAK=1 (N > 1): also time a
+batch of N x the batch size (`batch_x_gpus`: the work per GPU of the one-GPU run).
 """
 import argparse
 import json
@@ -452,6 +453,32 @@ def main():
         batch_4096 = {"queries_per_s": 4096 / (ms * 1e-3), "ms_per_batch": ms, "verify_kernel_ms": float(np.mean(ks)) * 1e-6,
                       "what": "the same measurement with round 1's batch of 4096 queries (device-resident), %d batches" % reps}
 
+    # ---- opt-in (VC_BENCH_WEAK=1), N > 1: the batch grown with the GPU count, i.e. the same work per GPU as the one-GPU run --------
+    # (`value` is strong scaling at a fixed batch; the search is bucket-stationary, so what a shard of N / G codes loses is the
+    # number of queries that share a bucket read - a batch of G x Q gives it back.  Not part of `value`.)
+    batch_x_gpus = None
+    if args.config == "headline" and mode == "mih" and world > 1 and os.environ.get("VC_BENCH_WEAK"):
+        QW = Q * world
+        big = torch.cat([dev_batches[i % len(dev_batches)] for i in range(world)])[:QW].contiguous()
+        for i in range(2):
+            searcher.search(big, K_NN, mode=mode)
+        barrier()
+        reps = 3
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ks, ss = [], []
+        s0.record()
+        for i in range(reps):
+            searcher.search(big, K_NN, mode=mode)
+            ks.append(ix.get_param("last_kernel_ns"))
+            ss.append(ix.get_param("mih.search_ns"))
+        s1.record()
+        barrier()
+        ms = max_over_ranks(s0.elapsed_time(s1) / reps)
+        batch_x_gpus = {"batch": QW, "queries_per_s": QW / (ms * 1e-3), "ms_per_batch": ms, "verify_kernel_ms": float(np.mean(ks)) * 1e-6,
+                        "search_ms_this_rank": float(np.mean(ss)) * 1e-6,
+                        "what": "batch = %d x %d GPUs (work per GPU as in the one-GPU run: weak scaling), device-resident, %d batches" % (Q, world, reps)}
+        del big
+
     # ---- the reference's approximate mode (search_worker.cc:93-157: stop at 20 k distinct candidates) on the same index, one GPU ------
     approximate_mode = None
     if args.config == "headline" and mode == "mih" and world == 1:
@@ -653,6 +680,8 @@ def main():
         }
         if args.config != "headline":
             line["sweep"] = sweep_rows
+        if batch_x_gpus is not None:
+            line["batch_x_gpus"] = batch_x_gpus
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     searcher.close()
     ix.close()

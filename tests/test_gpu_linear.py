@@ -77,6 +77,39 @@ def test_linear_large_k(oracle):
     _run(oracle, 30_000, 64, 2, 2048)
 
 
+def test_ring_scan_repeated_256bit_k1000(oracle):
+    """The shape that exposed the stage-release race of the TMA-ring kernel (scan.cuh: a stage handed back to cp.async.bulk while
+    shared-memory loads of it were still in flight): 256-bit codes, k = 1000, three queries per CTA, two CTAs per SM.  It failed in
+    a quarter of the calls, so the same scan is repeated; every repetition must equal the oracle (ids, distances, order)."""
+    n, nq, k, nbytes = 300_000, 16, 1000, 32
+    codes = oracle.synth_codes(12345, 0, n, nbytes)
+    queries = codes[:nq].copy()
+    queries[:, 0] ^= 1
+    oid, od, oc = oracle.linear_search(codes, queries, k)
+    ix = capi.Index(256, 0)
+    ix.add(codes)
+    for rep in range(24):
+        ids, dists, counts = ix.search_linear(queries, k)
+        np.testing.assert_array_equal(dists, od, err_msg="repetition %d" % rep)
+        np.testing.assert_array_equal(ids, oid, err_msg="repetition %d" % rep)
+    assert ix.get_param("scan.last_batched") == 0
+    ix.close()
+
+
+def test_merge_topk_long_lists_heavy_ties(oracle):
+    # 8 and 31 lists whose entries crowd into three distances (the shards' top-k rows): the merge kernel selects by a distance
+    # histogram before it sorts (topk_compact_block), the k-th distance has more ties than k
+    rng = np.random.default_rng(11)
+    for n_lists, nq, k in [(8, 7, 100), (31, 3, 100), (8, 3, 40), (2, 4, 1000), (5, 2, 400)]:
+        dist = rng.choice(np.array([11, 12, 13], dtype=np.uint64), size=(n_lists, nq, k), p=[0.02, 0.08, 0.9])
+        ids = rng.permutation(n_lists * nq * k).astype(np.uint64).reshape(n_lists, nq, k)
+        lists = np.sort((dist << np.uint64(32)) | ids, axis=-1)
+        out = capi.merge_topk(0, lists, k)
+        for q in range(nq):
+            ref = oracle.merge_topk(lists[:, q, :], k)
+            np.testing.assert_array_equal(out[q, : ref.size], ref)
+
+
 def test_merge_topk_matches_oracle(oracle):
     rng = np.random.default_rng(3)
     n_lists, nq, k = 8, 5, 100

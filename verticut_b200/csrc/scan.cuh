@@ -238,8 +238,13 @@ __global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanPa
         }
       }
     }
+    // The stage is refilled by cp.async.bulk (async proxy) as soon as all consumer warps have released it, and these loads are
+    // generic-proxy reads that may still be in flight when a release issued right behind them lands: measured on 256-bit codes,
+    // k = 1000, two CTAs per SM - the other CTA's bitonic sorts keep the shared-memory pipe busy -, a quarter of the scans
+    // returned a few wrong distances (tools/flake_probe.py).  So: a proxy fence behind the loads, and the release only after the
+    // step's barrier below, when every consumer thread has used its registers (~1 % of the HBM-bound scan's bandwidth).
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s.empty[st]);          // stage may be refilled while we compute
     if (tid < nq_here && gt < s.qrec[tid * QS + 2 * W]) atomicMin(&s.qrec[tid * QS + 2 * W], gt);
     auto local_of = [&](int c) -> uint32_t {
       if constexpr (W == 1) return 2 * ((c / 2) * kScanThreads + tid) + (c & 1);
@@ -279,6 +284,7 @@ __global__ void __launch_bounds__(kScanCtaThreads) scan_topk_kernel(const ScanPa
     }
     // one barrier per step; it also tells every thread whether anything was appended
     const uint32_t any = consumer_sync_or(appended | careful);
+    if (lane == 0) mbar_arrive(&s.empty[st]);          // the stage may be refilled from here on
     if (!any) continue;
 
     // ---- step epilogue ---------------------------------------------------------------------------------

@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(TcCfg<W, CS>::THREADS, 1) bmih_verify_tc_kerne
 #pragma unroll
           for (int i = 0; i < W; ++i) { const uint2 v = rp[i]; cw[2 * i] = v.x; cw[2 * i + 1] = v.y; }
         }
+        tc_proxy_fence();              // the raw stage is refilled by cp.async.bulk (async proxy): these generic-proxy reads first (scan.cuh)
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[rs]);
         uint32_t o[16 * W];

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(kTc1Threads, 1) bmih_verify_tc1_kernel(const _
 #pragma unroll
           for (int i = 0; i < W; ++i) { const uint2 v = rp[i]; cw[2 * i] = v.x; cw[2 * i + 1] = v.y; }
         }
+        tc1_proxy_fence();             // the raw stage is refilled by cp.async.bulk (async proxy): these generic-proxy reads first (scan.cuh)
         mbar_arrive(&raw_empty[rs]);
         tc1_wait(&a_empty[as], ((g / AS) & 1) ^ 1);
         tc_store_row<W, Cfg::SBO>(sA + (size_t)as * Cfg::A_BYTES, e, cw, false);
