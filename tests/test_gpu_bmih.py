@@ -123,7 +123,7 @@ def test_batched_fixed_radius_large_k(oracle, bits, m, r, k):
     ix.close()
 
 
-@pytest.mark.parametrize("cap", [64, 150, 700])
+@pytest.mark.parametrize("cap", [64, 150, 700, 4096])      # 4096 (the default): long buffers, the settle kernel selects before it sorts
 def test_batched_overflow_redoes_only_the_overflowed_queries(oracle, cap):
     """A candidate buffer that overflows (forced here with a tiny mih.cap) takes that query - not the whole batch - through
     the per-query kernel; the answers stay exact either way."""

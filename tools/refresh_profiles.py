@@ -25,32 +25,36 @@ for src, dst in [(RN + "_bench_ref.json", "bench_ref_%s.json" % RN), (RN + "_lau
         shutil.copy(p, os.path.join(P, dst))
 
 # ---- ncu summary of the verify launches of one headline search ---------------------------------------------------
-tmp = os.path.join(P, "ncu_%s_headline.md" % RN)
-subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), tmp, os.path.join(G, RN + "_bmih_verify.ncu-rep")], check=True)
-
-
-def g(sec, key):
-    m = re.search(r"\| %s \| ([0-9.]+) \| (\w*)" % re.escape(key), sec)
-    return float(m.group(1)) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(m.group(2), 1)
-
-
-launches = []
-for sec in open(tmp).read().split("## %s_bmih_verify.ncu-rep" % RN)[1:]:
-    launches.append(dict(ms=g(sec, "gpu__time_duration.sum"), dram_read_bytes=g(sec, "dram__bytes_read.sum"), dram_write_bytes=g(sec, "dram__bytes_write.sum"),
-                         xu_pct=g(sec, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
-                         alu_pct=g(sec, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
-                         issue_active_pct=g(sec, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                         warps_active_pct=g(sec, "sm__warps_active.avg.pct_of_peak_sustained_active"),
-                         registers=g(sec, "launch__registers_per_thread")))
+rep = os.path.join(G, RN + "_bmih_verify.ncu-rep")
+t = None
 cfg = bj["config"]
-t = {"what": "DRAM traffic of the bmih_verify_kernel launches of ONE headline search under `ncu --set full --clock-control none` "
-             "(tools/measure.sh: python tools/probe.py mih %d %d reps=1, launches 7..9 = the third search)" % (cfg["n_codes"], cfg["batch"]),
-     "config": {"n_codes": cfg["n_codes"], "batch": cfg["batch"], "k": 100, "n_gpus": 1},
-     "launches": launches,
-     "traffic_bytes_per_search": sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in launches),
-     "algorithmic_bytes_per_search": bj["roofline"]["algorithmic_bytes_per_launch"]}
-t["traffic_over_algorithmic"] = t["traffic_bytes_per_search"] / t["algorithmic_bytes_per_search"]
-json.dump(t, open(os.path.join(P, "traffic_%s.json" % RN), "w"), indent=1)
+if os.path.exists(rep):      # (no new capture: the committed ncu summary and traffic file stay)
+    tmp = os.path.join(P, "ncu_%s_headline.md" % RN)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), tmp, os.path.join(G, RN + "_bmih_verify.ncu-rep")], check=True)
+
+
+    def g(sec, key):
+        m = re.search(r"\| %s \| ([0-9.]+) \| (\w*)" % re.escape(key), sec)
+        return float(m.group(1)) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3}.get(m.group(2), 1)
+
+
+    launches = []
+    for sec in open(tmp).read().split("## %s_bmih_verify.ncu-rep" % RN)[1:]:
+        launches.append(dict(ms=g(sec, "gpu__time_duration.sum"), dram_read_bytes=g(sec, "dram__bytes_read.sum"), dram_write_bytes=g(sec, "dram__bytes_write.sum"),
+                             xu_pct=g(sec, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                             alu_pct=g(sec, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                             issue_active_pct=g(sec, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                             warps_active_pct=g(sec, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                             registers=g(sec, "launch__registers_per_thread")))
+    cfg = bj["config"]
+    t = {"what": "DRAM traffic of the bmih_verify_kernel launches of ONE headline search under `ncu --set full --clock-control none` "
+                 "(tools/measure.sh: python tools/probe.py mih %d %d reps=1, launches 7..9 = the third search)" % (cfg["n_codes"], cfg["batch"]),
+         "config": {"n_codes": cfg["n_codes"], "batch": cfg["batch"], "k": 100, "n_gpus": 1},
+         "launches": launches,
+         "traffic_bytes_per_search": sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in launches),
+         "algorithmic_bytes_per_search": bj["roofline"]["algorithmic_bytes_per_launch"]}
+    t["traffic_over_algorithmic"] = t["traffic_bytes_per_search"] / t["algorithmic_bytes_per_search"]
+    json.dump(t, open(os.path.join(P, "traffic_%s.json" % RN), "w"), indent=1)
 
 # ---- launch list of the first timed step -----------------------------------------------------------------------
 rows = [r for r in csv.reader(open(os.path.join(P, "launches_bench_%s.csv" % RN))) if len(r) > 10]
@@ -87,4 +91,5 @@ out.append("\nThe same step timed with CUDA events inside bench.py (no profiler,
            "the share agrees (ncu: %.1f %%)." % (RN, bj["ms_per_step"], bj["roofline"]["kernel_ms"], 100 * bj["roofline"]["kernel_ms"] / bj["ms_per_step"], 100 * vms / tot))
 open(os.path.join(P, "launches_step_%s.md" % RN), "w").write("\n".join(out) + "\n")
 print("\n".join(out))
-print(json.dumps({k: v for k, v in t.items() if k != "launches"}, indent=0))
+if t is not None:
+    print(json.dumps({k: v for k, v in t.items() if k != "launches"}, indent=0))
