@@ -229,3 +229,72 @@ def test_batched_approximate_equals_per_query_kernel_on_long_buckets(oracle):
     for f in ("radius", "n_results", "probes", "candidates", "unique"):
         np.testing.assert_array_equal(a[3][f], b[3][f])
     ix.close()
+
+
+def _kth_and_answers(oracle, codes, q, k):
+    oid, od, oc = oracle.linear_search(codes, q, k)
+    return oid, od, od[:, k - 1]
+
+
+@pytest.mark.parametrize("bits,m,n,nq,k", [(64, 4, 400_000, 48, 50), (128, 8, 200_000, 24, 100)])
+def test_speculative_threshold_misses_are_redone_exactly(oracle, bits, m, n, nq, k):
+    """Speculative thresholds (bmih_decide_kernel): the starting threshold of every query is capped by a guess of its k-th
+    distance.  Whatever the guess - far too small, too small for some queries, exactly the largest k-th distance - the answers
+    are the oracle's: a query the guess was too small for is detected (fewer than k codes within it once everything within it has
+    been enumerated) and redone by the per-query kernel."""
+    codes = oracle.synth_codes(12345, 0, n, bits // 8)
+    q = oracle.synth_codes(67890, 0, nq, bits // 8)
+    q[:4] = codes[:4]
+    oid, od, kth = _kth_and_answers(oracle, codes, q, k)
+    ix = capi.Index(bits, m)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    for guess in (1, int(np.median(kth)) - 1, int(np.median(kth)), int(kth.max()) - 1, int(kth.max()), int(kth.max()) + 3):
+        ix.set_param("mih.spec_tau", guess)
+        ids, dists, counts, st = ix.search_mih(q, k)
+        assert ix.get_param("mih.last_batched") == 1 and ix.get_param("mih.last_spec_tau") == guess
+        misses = int((kth > guess).sum())
+        assert ix.get_param("mih.last_spec_fail") == misses, (guess, misses)
+        assert ix.get_param("mih.last_redo") == misses
+        np.testing.assert_array_equal(dists, od, err_msg="guess %d" % guess)
+        np.testing.assert_array_equal(ids, oid, err_msg="guess %d" % guess)
+        assert (st["n_results"] == k).all()
+    ix.close()
+
+
+def test_speculative_threshold_is_learned_and_leaves_the_statistics_alone(oracle):
+    """The guess is learned from the previous batch on the same index (its largest k-th distance + 1); a batch with a miss is
+    followed by one without a guess.  For queries the guess holds for, radius / probes / candidates are those of a search without
+    it (fixed step rhythm)."""
+    n, nq, k = 1_000_000, 64, 100
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    qa = oracle.synth_codes(67890, 0, nq, 8)
+    qb = oracle.synth_codes(24680, 0, nq, 8)
+    ix = capi.Index(64, 4)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    ix.set_param("mih.table_steps", 1)
+    ix.set_param("mih.speculate", 0)
+    plain = ix.search_mih(qb, k)
+    assert ix.get_param("mih.last_spec_tau") == -1
+    ix.set_param("mih.speculate", 1)
+    a = ix.search_mih(qa, k)
+    assert ix.get_param("mih.last_spec_tau") == -1                      # nothing learned yet
+    kth_a = int(a[1][:, k - 1].max())
+    b = ix.search_mih(qb, k)
+    assert ix.get_param("mih.last_spec_tau") == kth_a + 1
+    misses = int((plain[1][:, k - 1] > kth_a + 1).sum())
+    assert ix.get_param("mih.last_spec_fail") == misses
+    np.testing.assert_array_equal(b[0], plain[0])
+    np.testing.assert_array_equal(b[1], plain[1])
+    held = plain[1][:, k - 1] <= kth_a + 1
+    for f in ("radius", "n_results", "probes", "candidates"):
+        np.testing.assert_array_equal(b[3][f][held], plain[3][f][held])
+    oid, od, _ = oracle.linear_search(codes, qb, k)
+    np.testing.assert_array_equal(b[0], oid)
+    c = ix.search_mih(qa, k)                                              # after a miss: no guess; else the value learned from qb
+    assert ix.get_param("mih.last_spec_tau") == (-1 if misses else int(plain[1][:, k - 1].max()) + 1)
+    np.testing.assert_array_equal(c[0], a[0])
+    ix.close()

@@ -173,8 +173,8 @@ def test_interleaved_shards_equal_unsharded(oracle, G, mode):
     np.testing.assert_array_equal(counts, oc)
 
 
-@pytest.mark.parametrize("table_steps", [-1, 1])
-def test_two_shards_with_live_exchange(oracle, table_steps):
+@pytest.mark.parametrize("table_steps,spec_tau", [(-1, -1), (1, -1), (-1, 16), (1, 5)])
+def test_two_shards_with_live_exchange(oracle, table_steps, spec_tau):
     """Both collectives of the sharded batched search, matched between two shards that search at the same time (two
     host threads, one GPU): the per-step sum of the distance histograms and, before table-granular steps, the sum of the
     id histograms that bounds the k-th key of the whole database.  Merged result == oracle, exactly."""
@@ -194,6 +194,9 @@ def test_two_shards_with_live_exchange(oracle, table_steps):
         ix.build()
         ix.set_param("mih.batched", 1)
         ix.set_param("mih.table_steps", table_steps)
+        # a speculative threshold that is too small for some (16) or all (5) queries: the miss is decided on the SUMMED histograms,
+        # so both shards take the query out at the same step and redo it; the merged answer stays exact
+        ix.set_param("mih.spec_tau", spec_tau)
         ixs.append(ix)
 
     def make_hook(g):

@@ -131,6 +131,15 @@ struct vc_index {
   // the other buckets after them with the lower-bound filter: -1 = when the step has >= 2 queries per probed bucket, 0 never, 1 always.
   // Measured slower than one launch on the exact distance (batch 16384: 10.6 vs 9.9 ms; profiles/ab_r02.md): off.
   int64_t mih_r0_first = 0;
+  // speculative thresholds of the batched exact search (bmih_decide_kernel): the largest final k-th distance of the previous batch
+  // on this index, plus one, caps every query's starting threshold; a query it was too small for is redone, exactly.  Off by
+  // default: measured, it only helps where the first step is HBM-bound (1 B codes: -4 % per batch of 4096, nothing at 16 384, where
+  // the first step's cost is the lower bound's pass rate in the queries' own buckets, not the threshold; profiles/ab_r02.md 8)
+  int64_t mih_speculate = 0;      // knob "mih.speculate": 1 on
+  int64_t mih_spec_force = -1;    // knob "mih.spec_tau": >= 0 forces this guess (tests), -1 learns it
+  bool spec_valid = false;
+  uint32_t spec_tau = 0, spec_k = 0;
+  int64_t last_spec_tau = -1, last_spec_fail = 0;
   int64_t mih_split_r0 = 0;       // 1: radius 0 is a search step of its own (tighter thresholds for radius 1) instead of being probed together with radius 1
   int64_t mih_cap = 0;            // candidate-buffer entries per query (0: bmih_cap_for(k)); small values force the overflow path in tests
   int64_t mih_global_key = 1;     // id-sharded search: exchange a bound on the k-th key of the whole database before table-granular steps
@@ -470,7 +479,7 @@ int vc_index_build(vc_index* ix) {
   if (!ix->d_codes) { int rc = reserve_codes(ix, 1); if (rc) return rc; }
   int rc = ix->W == 1 ? build_tables_impl<1>(ix) : ix->W == 2 ? build_tables_impl<2>(ix) : build_tables_impl<4>(ix);
   if (rc) { free_tables(ix); return rc; }
-  ix->built = true; ix->max_bucket_len = 0;
+  ix->built = true; ix->max_bucket_len = 0; ix->spec_valid = false;
   return VC_OK;
 }
 
@@ -602,7 +611,7 @@ int vc_index_load(int device, const char* path, vc_index** out) {
     else if (!rc && bad) rc = fail(VC_ERR_ARG, "corrupt index file: a bucket directory is not a non-decreasing sequence ending at the code count");
   }
   if (rc) { vc_index_destroy(ix); return rc; }
-  ix->built = true; ix->max_bucket_len = 0;
+  ix->built = true; ix->max_bucket_len = 0; ix->spec_valid = false;
   *out = ix;
   return VC_OK;
 }
@@ -786,6 +795,7 @@ static int scan_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32
   BmihParams p;
   memset(&p, 0, sizeof p);
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = 1; p.sbits = 0; p.max_radius = 0; p.cap = cap;
+  p.spec_tau = kInfDist;
   p.scan_mode = 1; p.first_id = ix->first_id; p.id_stride = ix->id_stride;
   p.pf_tau = ix->scan_prefilter > 0 ? 0x7FFFFFFFu : bmih_pf_tau(W, 0, true);
   TableDev pseudo;
@@ -1135,6 +1145,12 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   BmihParams p;
   memset(&p, 0, sizeof p);
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = m; p.sbits = sbits; p.radius = 0; p.max_radius = max_radius; p.cap = cap;
+  p.spec_tau = kInfDist; p.spec_fail = ctr + 25;
+  if (max_radius < 0) {
+    if (ix->mih_spec_force >= 0) p.spec_tau = (uint32_t)ix->mih_spec_force;
+    else if (ix->mih_speculate > 0 && ix->spec_valid && ix->spec_k == k) p.spec_tau = ix->spec_tau;
+  }
+  ix->last_spec_tau = p.spec_tau == kInfDist ? -1 : (int64_t)p.spec_tau; ix->last_spec_fail = 0;
   p.tables = ix->d_tab; p.active = nullptr; p.n_active = 0;
   {
     // work-item length: about one average bucket, between 2 and 8 CTA steps
@@ -1209,7 +1225,9 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   int verify_grid = 0;
   int levels = 0;
   int64_t items_total = 0;
-  bool loose_majority = true;           // thresholds straight from the bootstrap
+  // thresholds straight from the bootstrap are loose - unless the speculative bound (the previous batch's largest k-th distance + 1)
+  // caps them below what the lower-bound filter needs (bmih_pf_tau)
+  bool loose_majority = !(p.spec_tau != kInfDist && p.spec_tau < p.pf_tau);
   // steps: (radius r, tables [t0, t1)).  A whole radius per step, or - when most queries are about to stop - one
   // table per step, so that the strict rule d_k <= m*r + t can end the search in the middle of a radius.
   uint32_t r = 0, t0 = 0;
@@ -1389,6 +1407,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
     }
   }
   if (ix->profile) { ix->lev_used = std::min(levels, 34); ix->ev_valid = true; }
+  if (max_radius < 0) {                 // the next batch's speculative threshold: this batch's largest final k-th distance
+    bmih_maxtau_kernel<<<(nq + 255) / 256, 256, 0, st>>>(p, ctr + 24);
+    ix->launches++;
+  }
   // sharded call over peer memory (vc_search_sharded_dev): unless some query has to be redone below, the finish kernel
   // itself stores the result rows into every shard's window
   ix->x_pushed = false;
@@ -1417,9 +1439,19 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   }
   CU(cudaGetLastError());
   unsigned long long h_bc = 0, tcs[3] = {0, 0, 0};
+  uint32_t h_spec[2] = {0, 0};          // [0] largest final k-th distance, [1] queries the speculative threshold was too small for
   CU(cudaMemcpyAsync(&h_bc, p.bucket_codes, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(tcs, p.tc_stats, 24, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_spec, ctr + 24, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if (max_radius < 0) {
+    // learn only from a batch in which the guess held for every query (a miss means the data moved: one batch without a guess
+    // follows, which sees every k-th distance again); id-sharded: thresholds and misses come from the summed histograms, so
+    // every shard learns the same value
+    ix->last_spec_fail = h_spec[1];
+    ix->spec_valid = h_spec[1] == 0 && h_spec[0] > 0 && h_spec[0] <= 64u * W;
+    ix->spec_tau = h_spec[0] + 1; ix->spec_k = k;
+  }
   ix->tc_units = (int64_t)tcs[0]; ix->tc_flagged = (int64_t)tcs[1]; ix->tc_hits = (int64_t)tcs[2];
   ix->last_mih_batched = 1; ix->last_mih_levels = levels; ix->last_mih_items = items_total; ix->last_mih_bucket_codes = (int64_t)h_bc;
   return VC_OK;
@@ -1706,6 +1738,8 @@ int vc_index_set_param(vc_index* ix, const char* name, int64_t value) {
   else if (!strcmp(name, "xchg.emulate")) ix->x_emulate = value;
   else if (!strcmp(name, "mih.boot_sample")) ix->mih_boot_sample = value;
   else if (!strcmp(name, "mih.split_r0")) ix->mih_split_r0 = value;
+  else if (!strcmp(name, "mih.speculate")) { ix->mih_speculate = value; ix->spec_valid = false; }
+  else if (!strcmp(name, "mih.spec_tau")) ix->mih_spec_force = value;
   else if (!strcmp(name, "mih.r0_first")) ix->mih_r0_first = value;
   else if (!strcmp(name, "mih.cap")) {
     if (value < 0 || value > (1 << 20)) return fail(VC_ERR_ARG, "mih.cap must be in [0, 2^20]");
@@ -1760,6 +1794,9 @@ int vc_index_get_param(const vc_index* ix, const char* name, int64_t* value) {
   else if (!strcmp(name, "mih.last_batched")) *value = ix->last_mih_batched;
   else if (!strcmp(name, "mih.last_levels")) *value = ix->last_mih_levels;
   else if (!strcmp(name, "mih.last_redo")) *value = ix->last_mih_redo;
+  else if (!strcmp(name, "mih.speculate")) *value = ix->mih_speculate;
+  else if (!strcmp(name, "mih.last_spec_tau")) *value = ix->last_spec_tau;      // the speculative threshold of the last batched search (-1: none)
+  else if (!strcmp(name, "mih.last_spec_fail")) *value = ix->last_spec_fail;    // queries it was too small for (redone by the per-query kernel)
   else if (!strcmp(name, "xchg")) *value = ix->x_enabled;
   else if (!strcmp(name, "xchg.open")) *value = ix->x_open ? 1 : 0;
   else if (!strcmp(name, "xchg.last")) *value = ix->last_xchg;

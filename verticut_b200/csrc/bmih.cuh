@@ -81,6 +81,8 @@ struct BmihParams {
   uint32_t cap;                 // candidate-buffer entries per query (bmih_cap_for(k))
   uint32_t pf_tau;              // thresholds (less the probing radius) >= this count as loose: the lower-bound filter would pass too much (bmih_pf_tau)
   uint32_t boot_sample;         // codes per query the threshold bootstrap looks at (0: the default)
+  uint32_t spec_tau;            // speculative bound of every query's k-th distance (kInfDist: none), see bmih_decide_kernel
+  uint32_t* spec_fail;          // [1] queries whose k-th distance turned out to lie above it (they are redone)
   uint32_t count_in_write;      // items kernel: the writing pass is the only pass, it also keeps the statistics
   uint32_t qt;                  // queries per work item (kBmihQT for the POPC kernel, up to 256 for the tensor-core kernel)
   uint32_t cpi_alt, qt_alt;     // counting pass only: the item geometry of the other verify kernel ...
@@ -810,11 +812,19 @@ __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uin
   const uint32_t r = p.radius;
   const bool level_done = p.t_end == p.m;                                                // a whole radius is finished
   bool stop = false;
+  // Speculative thresholds (p.spec_tau, api.cu: the largest k-th distance of the previous batch on this index, plus one): the
+  // filter started at min(bootstrap, spec_tau) instead of the bootstrap's looser bound.  If that guess was too small for this
+  // query, fewer than k codes passed - and once every code within spec_tau has been enumerated (distance bound of what is left
+  // > spec_tau) that is certain: the query leaves the batched search like an overflowed one and is answered by the per-query
+  // kernel, exactly.  A query with k codes within spec_tau never notices: nothing at or below its k-th distance was filtered.
+  const bool spec_failed = p.spec_tau != kInfDist && p.max_radius < 0 && tau == kInfDist && p.spec_tau + 1 <= p.m * r + p.t_end;
+  const uint32_t tau_likely = min(tau, p.spec_tau);                                      // where the query will end if the guess holds
   if (level_done) {
     stop = r >= p.sbits;
     if (p.max_radius >= 0) stop = stop || r >= (uint32_t)p.max_radius;
   }
   if (p.max_radius < 0) stop = stop || (tau != kInfDist && tau + 1 <= p.m * r + p.t_end);
+  if (spec_failed) { atomicOr(&p.gflag[q], 1u); *any_overflow = 1; stop = true; atomicAdd(p.spec_fail, 1u); }
   p.gradius[q] = r;
   for (uint32_t rr = p.r_lo; rr <= r; ++rr)
     p.gprobes[q] += (unsigned long long)(p.t_end - p.t_begin) * c_binom[p.sbits][rr];    // n_sub_reads_ of this step
@@ -822,7 +832,7 @@ __global__ void bmih_decide_kernel(const BmihParams p, const uint32_t* list, uin
   // leaves the batched search now - on every shard at the same step - and is answered by the per-query kernel afterwards
   if (xhist[(size_t)q * HB + HB - 1]) { atomicOr(&p.gflag[q], 1u); *any_overflow = 1; stop = true; }
   // would this query stop somewhere inside the next radius even if tau did not improve any more?
-  if (!stop && level_done && tau != kInfDist && tau + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
+  if (!stop && level_done && tau_likely != kInfDist && tau_likely + 1 <= p.m * (r + 1) + p.m) atomicAdd(n_likely, 1u);
   if (stop) atomicOr(&p.gflag[q], 2u);
   else {
     p.next_active[atomicAdd(p.n_next, 1u)] = q;
@@ -873,11 +883,20 @@ __global__ void bmih_idcut_kernel(const BmihParams p, const uint32_t* list, uint
   if (bound < p.gtaukey[q]) p.gtaukey[q] = bound;
 }
 
+// largest final k-th distance of the queries the batched search answered itself (the next batch's speculative threshold)
+__global__ void bmih_maxtau_kernel(const BmihParams p, uint32_t* out) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t v = 0;
+  if (q < p.nq && !(p.gflag[q] & 1u)) v = p.gtau[q];                 // kInfDist (no k codes found at all) makes the guess void
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
 // per-query state at the start of a search
 __global__ void bmih_init_kernel(const BmihParams p, uint32_t* active0) {
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= p.nq) return;
-  p.gcnt[q] = 0; p.gtau[q] = kInfDist; p.gtaukey[q] = kEmptyKey; if (p.gglobkey) p.gglobkey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
+  p.gcnt[q] = 0; p.gtau[q] = p.spec_tau; p.gtaukey[q] = kEmptyKey; if (p.gglobkey) p.gglobkey[q] = kEmptyKey; p.gflag[q] = 0; p.gradius[q] = 0;
   p.gprobes[q] = 0; p.gcands[q] = 0;
   active0[q] = q;
 }
@@ -941,7 +960,7 @@ __global__ void __launch_bounds__(256) bmih_bootstrap_kernel(const BmihParams p,
     uint32_t cum = 0;
     for (uint32_t d = 0; d <= 64 * W; ++d) {
       cum += h[d];
-      if (cum >= p.k) { p.gtau[q] = d; break; }
+      if (cum >= p.k) { p.gtau[q] = min(d, p.spec_tau); break; }
     }
   }
 }
