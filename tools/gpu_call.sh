@@ -1,15 +1,8 @@
 #!/bin/bash
-# scratch: the command list of the current gpurun call
+# scratch: the command list of the current gpurun call (2 GPUs)
 mkdir -p gpurun_out
-T=r02b
-{
-  for sp in 0 1; do
-    timeout 200 python tools/probe.py mih 1000000000 16384 check=16 reps=4 mih.speculate=$sp 2>&1 | tail -1
-    timeout 200 python tools/probe.py mih 1000000000 4096 reps=4 mih.speculate=$sp 2>&1 | tail -1
-    timeout 200 python tools/probe.py mih 125000000 16384 shards=8 reps=4 mih.speculate=$sp 2>&1 | tail -1
-    timeout 200 python tools/probe.py mih 100000000 4096 reps=4 mih.speculate=$sp 2>&1 | tail -1
-    timeout 200 python tools/probe.py mih 125000000 4096 bits=128 m=8 reps=3 mih.speculate=$sp 2>&1 | tail -1
-  done
-} > gpurun_out/${T}_spec1.log 2>&1
-cut -c1-700 gpurun_out/${T}_spec1.log
-timeout 600 python -m pytest tests/test_gpu_bmih.py tests/test_gpu_sharded.py tests/test_gpu_mih.py -x -q > gpurun_out/${T}_pytest4.log 2>&1; tail -n 15 gpurun_out/${T}_pytest4.log
+T=r02c
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+export VC_BENCH_SKIP_BIG_SCAN=1
+timeout 300 python -m pytest tests/test_gpu_nccl.py -x -q > gpurun_out/${T}_pytest2.log 2>&1; tail -n 2 gpurun_out/${T}_pytest2.log
+timeout 300 $TR --master-port 29621 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/${T}_bench2.json 2> gpurun_out/${T}_bench2.err; tail -1 gpurun_out/${T}_bench2.err; head -c 300 gpurun_out/${T}_bench2.json; echo
