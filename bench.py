@@ -556,6 +556,12 @@ def main():
                               "bound": "hbm" if t_hbm > t_popc else "popc", "tests_executed": sx, "bucket_members_x_queries": sp})
                 bound_s += max(t_hbm, t_popc)
                 meas_s += sn
+            roofline["which_bound_binds"] = (
+                "`frac` is achieved / peak on the HBM axis, as the bench contract defines it; with %d queries per batch a probed bucket is read "
+                "once for %.0f queries on average, so %d of the %d search steps are bound by the integer (POPC) pipe, not by HBM - north_star's "
+                "roofline (the slower of the code bytes at HBM speed and the popcount work at integer-pipe peak, per step) is `combined.frac`" % (
+                    Q, sum(x["bucket_members_x_queries"] for x in steps) / max(1.0, float(sum(ix.get_param("mih.step_codes.%d" % i) for i in range(n_steps)))),
+                    sum(1 for x in steps if x["bound"] == "popc"), n_steps))
             roofline["combined"] = {"what": "sum over search steps of max(HBM time, POPC time) / measured verify-kernel time; "
                                             "%d POPC per test, POPC peak %.1f / clk / SM (tools/microbench.cu)" % (popc_per_pair, POPC_PER_CLK_PER_SM),
                                     "bound_ms": bound_s * 1e3, "measured_ms": meas_s * 1e3, "frac": bound_s / meas_s, "steps": steps}

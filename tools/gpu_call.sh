@@ -1,8 +1,10 @@
 #!/bin/bash
-# scratch: the command list of the current gpurun call (2 GPUs)
+# scratch: the command list of the current gpurun call
 mkdir -p gpurun_out
 T=r02c
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-export VC_BENCH_SKIP_BIG_SCAN=1
-timeout 300 python -m pytest tests/test_gpu_nccl.py -x -q > gpurun_out/${T}_pytest2.log 2>&1; tail -n 2 gpurun_out/${T}_pytest2.log
-timeout 300 $TR --master-port 29621 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/${T}_bench2.json 2> gpurun_out/${T}_bench2.err; tail -1 gpurun_out/${T}_bench2.err; head -c 300 gpurun_out/${T}_bench2.json; echo
+VC_BENCH_SKIP_CPU=1 VC_BENCH_SKIP_BIG_SCAN=1 timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/${T}_bench_note.json 2> gpurun_out/${T}_bench_note.err; echo rc=$?; tail -n 3 gpurun_out/${T}_bench_note.err
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r02c_bench_note.json').read().strip().splitlines()[-1])
+print(d["value"], d["roofline"]["which_bound_binds"])
+P
