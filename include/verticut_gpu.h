@@ -208,7 +208,8 @@ int vc_search_sharded_dev(vc_index* ix, int mih, const void* d_queries, uint32_t
  *                 distance filter through it (off: measured slower)
  *   "mih.speculate" = 1 (default 0): the batched exact search caps every query's starting threshold by the largest k-th distance
  *                 of the previous batch on this index, plus one; a query the guess is too small for is detected and redone exactly
- *                 ("mih.spec_tau" >= 0 forces a guess; "mih.last_spec_tau" / "mih.last_spec_fail" report it)
+ *                 ("mih.spec_tau" >= 0 forces a guess; "mih.last_spec_tau" / "mih.last_spec_fail" report it; id-sharded: the same
+ *                 setting on every rank - the guess and its misses are then derived from the summed histograms and agree)
  *   "host.chunk"  vc_search_linear / vc_search_mih pass their queries through the device in batches of this many (32 768)
  *   "xchg", "xchg.allreduce", "xchg.emulate"   the peer-memory exchange of an id-sharded search
  *   "profile", "last_kernel_ns", "launches", "mih.step_*", "tc.last_*"   read-back of timings and statistics */
