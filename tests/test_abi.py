@@ -72,3 +72,17 @@ def test_nccl_hook_marshals_an_in_place_uint32_sum():
     seen["rc"] = 5
     assert L.vc_nccl_allreduce_hook(user, C.c_void_p(0x7000), 1, None) != 0 and b"ncclAllReduce" in L.vc_last_error()
     assert L.vc_nccl_allreduce_hook(None, C.c_void_p(0x7000), 1, None) != 0
+
+
+def test_tools_and_bench_compile_and_stay_off_the_oracle():
+    """tools/*.py run on the GPU box only: at least they must parse here, and - like the product - the measurement tools compare
+    with numpy or with another GPU path, never with oracle/ (only tests/, smoke() and bench.py's CPU legs may use it)."""
+    import glob
+    import py_compile
+    paths = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(paths) >= 10
+    for p in paths:
+        py_compile.compile(p, doraise=True)
+    for p in glob.glob(os.path.join(ROOT, "tools", "*.py")):
+        src = open(p).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), "%s imports the oracle" % p
