@@ -264,7 +264,7 @@ def test_speculative_threshold_misses_are_redone_exactly(oracle, bits, m, n, nq,
 
 
 def test_speculative_threshold_is_learned_and_leaves_the_statistics_alone(oracle):
-    """The guess is learned from the previous batch on the same index (its largest k-th distance + 1); a batch with a miss is
+    """The guess is learned from the previous batch on the same index (its largest k-th distance); a batch with a miss is
     followed by one without a guess.  For queries the guess holds for, radius / probes / candidates are those of a search without
     it (fixed step rhythm)."""
     n, nq, k = 1_000_000, 64, 100
@@ -279,22 +279,53 @@ def test_speculative_threshold_is_learned_and_leaves_the_statistics_alone(oracle
     ix.set_param("mih.speculate", 0)
     plain = ix.search_mih(qb, k)
     assert ix.get_param("mih.last_spec_tau") == -1
-    ix.set_param("mih.speculate", 1)
+    ix.set_param("mih.speculate", 2)                                     # 1 (the default) speculates on batches of >= 1024 queries only
     a = ix.search_mih(qa, k)
     assert ix.get_param("mih.last_spec_tau") == -1                      # nothing learned yet
     kth_a = int(a[1][:, k - 1].max())
     b = ix.search_mih(qb, k)
-    assert ix.get_param("mih.last_spec_tau") == kth_a + 1
-    misses = int((plain[1][:, k - 1] > kth_a + 1).sum())
+    assert ix.get_param("mih.last_spec_tau") == kth_a
+    misses = int((plain[1][:, k - 1] > kth_a).sum())
     assert ix.get_param("mih.last_spec_fail") == misses
     np.testing.assert_array_equal(b[0], plain[0])
     np.testing.assert_array_equal(b[1], plain[1])
-    held = plain[1][:, k - 1] <= kth_a + 1
+    held = plain[1][:, k - 1] <= kth_a
     for f in ("radius", "n_results", "probes", "candidates"):
         np.testing.assert_array_equal(b[3][f][held], plain[3][f][held])
     oid, od, _ = oracle.linear_search(codes, qb, k)
     np.testing.assert_array_equal(b[0], oid)
     c = ix.search_mih(qa, k)                                              # after a miss: no guess; else the value learned from qb
-    assert ix.get_param("mih.last_spec_tau") == (-1 if misses else int(plain[1][:, k - 1].max()) + 1)
+    assert ix.get_param("mih.last_spec_tau") == (-1 if misses else int(plain[1][:, k - 1].max()))
     np.testing.assert_array_equal(c[0], a[0])
+    ix.close()
+
+
+def test_speculation_by_default_on_large_batches_stays_exact(oracle):
+    """mih.speculate = 1 (the default) learns from and applies to batches of >= 1024 queries: three such batches of different queries
+    on one index - the second and third start from the previous one's largest k-th distance, and whichever queries that is too small
+    for are redone - all equal to the oracle; a small batch in between neither uses nor changes the guess."""
+    n, nq, k = 300_000, 1024, 20
+    codes = oracle.synth_codes(12345, 0, n, 8)
+    ix = capi.Index(64, 4)
+    ix.add(codes)
+    ix.build()
+    ix.set_param("mih.batched", 1)
+    assert ix.get_param("mih.speculate") == 1
+    prev_max = -1
+    for b, seed in enumerate((67890, 24680, 13579)):
+        q = oracle.synth_codes(seed, 0, nq, 8)
+        oid, od, _ = oracle.linear_search(codes, q, k)
+        ids, dists, counts, st = ix.search_mih(q, k)
+        assert ix.get_param("mih.last_batched") == 1
+        guess = ix.get_param("mih.last_spec_tau")
+        assert guess == prev_max, (b, guess, prev_max)
+        misses = int((od[:, k - 1] > guess).sum()) if guess >= 0 else 0
+        assert ix.get_param("mih.last_spec_fail") == misses
+        np.testing.assert_array_equal(dists, od, err_msg="batch %d" % b)
+        np.testing.assert_array_equal(ids, oid, err_msg="batch %d" % b)
+        prev_max = -1 if misses else int(od[:, k - 1].max())      # a batch with a miss teaches nothing
+        if b == 0:                                                 # a small batch: no guess used, none learned
+            small = ix.search_mih(q[:8], k)
+            assert ix.get_param("mih.last_spec_tau") == -1
+            np.testing.assert_array_equal(small[0], oid[:8])
     ix.close()

@@ -132,10 +132,11 @@ struct vc_index {
   // Measured slower than one launch on the exact distance (batch 16384: 10.6 vs 9.9 ms; profiles/ab_r02.md): off.
   int64_t mih_r0_first = 0;
   // speculative thresholds of the batched exact search (bmih_decide_kernel): the largest final k-th distance of the previous batch
-  // on this index, plus one, caps every query's starting threshold; a query it was too small for is redone, exactly.  Off by
-  // default: measured, it only helps where the first step is HBM-bound (1 B codes: -4 % per batch of 4096, nothing at 16 384, where
-  // the first step's cost is the lower bound's pass rate in the queries' own buckets, not the threshold; profiles/ab_r02.md 8)
-  int64_t mih_speculate = 0;      // knob "mih.speculate": 1 on
+  // on this index caps every query's starting threshold; a query it was too small for is detected and redone, exactly.  Measured
+  // (profiles/spec_r02.log): 1 B codes, batch 16 384: first step 9.96 -> 7.23 ms, the search 51.5 -> 48.7 ms.  Learned from and
+  // applied to LARGE batches only (>= kSpecMinBatch queries): a handful of queries says little about the next batch's largest k-th
+  // distance, and a guess that is too small sends its misses through the per-query kernel
+  int64_t mih_speculate = 1;      // knob "mih.speculate": 0 off, 1 batches of >= 1024 queries, 2 every batch (tests)
   int64_t mih_spec_force = -1;    // knob "mih.spec_tau": >= 0 forces this guess (tests), -1 learns it
   bool spec_valid = false;
   uint32_t spec_tau = 0, spec_k = 0;
@@ -1123,6 +1124,7 @@ static int scan_inplace_small(vc_index* ix, uint32_t* d, uint64_t n, uint32_t* s
 }
 
 // Bucket-stationary batched MIH (bmih.cuh).  Exact or fixed-radius search over dense tables.
+constexpr uint32_t kSpecMinBatch = 1024;     // speculative thresholds: batches smaller than this neither use nor teach a guess (mih.speculate = 1)
 template <int W>
 static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_t k, int max_radius,
                        uint64_t* d_out_keys, vc_query_stats* d_stats, cudaStream_t st) {
@@ -1146,9 +1148,10 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   memset(&p, 0, sizeof p);
   p.queries = (const uint32_t*)d_queries; p.nq = nq; p.k = k; p.m = m; p.sbits = sbits; p.radius = 0; p.max_radius = max_radius; p.cap = cap;
   p.spec_tau = kInfDist; p.spec_fail = ctr + 25;
+  const bool spec_batch = max_radius < 0 && (ix->mih_speculate >= 2 || (ix->mih_speculate == 1 && nq >= kSpecMinBatch));
   if (max_radius < 0) {
     if (ix->mih_spec_force >= 0) p.spec_tau = (uint32_t)ix->mih_spec_force;
-    else if (ix->mih_speculate > 0 && ix->spec_valid && ix->spec_k == k) p.spec_tau = ix->spec_tau;
+    else if (spec_batch && ix->spec_valid && ix->spec_k == k) p.spec_tau = ix->spec_tau;
   }
   ix->last_spec_tau = p.spec_tau == kInfDist ? -1 : (int64_t)p.spec_tau; ix->last_spec_fail = 0;
   p.tables = ix->d_tab; p.active = nullptr; p.n_active = 0;
@@ -1444,13 +1447,13 @@ static int mih_batched(vc_index* ix, const void* d_queries, uint32_t nq, uint32_
   CU(cudaMemcpyAsync(tcs, p.tc_stats, 24, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(h_spec, ctr + 24, 8, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if (max_radius < 0) {
+  if (max_radius < 0) ix->last_spec_fail = h_spec[1];
+  if (spec_batch) {
     // learn only from a batch in which the guess held for every query (a miss means the data moved: one batch without a guess
     // follows, which sees every k-th distance again); id-sharded: thresholds and misses come from the summed histograms, so
     // every shard learns the same value
-    ix->last_spec_fail = h_spec[1];
     ix->spec_valid = h_spec[1] == 0 && h_spec[0] > 0 && h_spec[0] <= 64u * W;
-    ix->spec_tau = h_spec[0] + 1; ix->spec_k = k;
+    ix->spec_tau = h_spec[0]; ix->spec_k = k;      // no slack: one more unit of threshold triples the first step's hits (profiles/spec_r02.log)
   }
   ix->tc_units = (int64_t)tcs[0]; ix->tc_flagged = (int64_t)tcs[1]; ix->tc_hits = (int64_t)tcs[2];
   ix->last_mih_batched = 1; ix->last_mih_levels = levels; ix->last_mih_items = items_total; ix->last_mih_bucket_codes = (int64_t)h_bc;
