@@ -1,4 +1,4 @@
 #!/bin/bash
 # scratch: the command list of the current gpurun call
 mkdir -p gpurun_out
-timeout 80 python -m pytest tests/test_gpu_bmih.py -x -q -k "speculation_by_default" > gpurun_out/r02d_pytest2.log 2>&1; tail -n 12 gpurun_out/r02d_pytest2.log
+timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/r02d_bench_final.json 2> gpurun_out/r02d_bench_final.err; echo rc=$?; tail -n 1 gpurun_out/r02d_bench_final.err | cut -c1-200; cut -c1-200 gpurun_out/r02d_bench_final.json
