@@ -206,8 +206,9 @@ int vc_search_sharded_dev(vc_index* ix, int mih, const void* d_queries, uint32_t
  *                 "mih.table_steps", "mih.global_key"; "scan.tc" = -1 (default): 64-bit scans of >= "scan.tc_min" (256) queries
  *                 over >= 2^29 codes use the tensor-core kernel, 0 never, 1 / 2 force a version; "mih.tc" = 1 routes the MIH
  *                 distance filter through it (off: measured slower)
- *   "mih.speculate" = 1 (default 0): the batched exact search caps every query's starting threshold by the largest k-th distance
- *                 of the previous batch on this index, plus one; a query the guess is too small for is detected and redone exactly
+ *   "mih.speculate" = 1 (default; 0 off, 2 also for batches below 1024 queries): the batched exact search caps every query's
+ *                 starting threshold by the largest k-th distance of the previous (large) batch on this index; a query the guess
+ *                 is too small for is detected and redone exactly
  *                 ("mih.spec_tau" >= 0 forces a guess; "mih.last_spec_tau" / "mih.last_spec_fail" report it; id-sharded: the same
  *                 setting on every rank - the guess and its misses are then derived from the summed histograms and agree)
  *   "host.chunk"  vc_search_linear / vc_search_mih pass their queries through the device in batches of this many (32 768)
