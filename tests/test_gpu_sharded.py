@@ -258,6 +258,7 @@ def _peer_rank(rank, G, n, nq, k, conns, ret):
     ix.add_synthetic(cnt, 12345)
     ix.build()
     ix.set_param("mih.batched", 1)
+    ix.set_param("mih.speculate", 2)                    # learned speculative thresholds for these small batches too (the default: >= 1024 queries)
     mine = ix.xchg_create(rank, G, 4 << 20)
     for c in conns:                                     # full exchange of the 64-byte IPC handles
         c.send((rank, mine))
@@ -266,13 +267,18 @@ def _peer_rank(rank, G, n, nq, k, conns, ret):
         r, h = c.recv()
         handles[r] = h
     ix.xchg_open(b"".join(handles[r] for r in range(G)))
-    outs = [torch.empty((nq, k), dtype=torch.int64, device="cuda") for _ in range(3)]
+    outs = [torch.empty((nq, k), dtype=torch.int64, device="cuda") for _ in range(4)]
     ix.search_sharded_dev(True, dq.data_ptr(), nq, k, outs[0].data_ptr())
     n_x = ix.get_param("xchg.last")
     ix.search_sharded_dev(False, dq.data_ptr(), nq, k, outs[1].data_ptr())
     ix.search_sharded_dev(True, dq.data_ptr(), nq, k, outs[2].data_ptr(), max_radius=1)
+    # other queries: this search starts from the guess the first one taught (the largest k-th distance of the WHOLE database's
+    # answers - both ranks learn the same value from the summed histograms); queries it is too small for are redone on both ranks
+    dq2 = torch.from_numpy(R.synth_codes(24680, 0, nq, 8)).cuda()
+    ix.search_sharded_dev(True, dq2.data_ptr(), nq, k, outs[3].data_ptr())
+    spec = (ix.get_param("mih.last_spec_tau"), ix.get_param("mih.last_spec_fail"))
     torch.cuda.synchronize()
-    ret[rank] = ([o.cpu().numpy().view(np.uint64).copy() for o in outs], n_x)
+    ret[rank] = ([o.cpu().numpy().view(np.uint64).copy() for o in outs], n_x, spec)
     for c in conns:                                     # nobody closes its window while a peer may still store into it
         c.send("done")
     for c in conns:
@@ -304,9 +310,14 @@ def test_two_shards_over_peer_windows(oracle):
         assert p.exitcode == 0, "rank process failed (exit code %s)" % p.exitcode
     want = oracle.scan_synth(12345, 0, 1, n, 8, queries, k, n_procs=4)
     want_r1 = oracle.scan_synth(12345, 0, 1, n, 8, queries, k, m=4, max_radius=1, n_procs=4)
+    want2 = oracle.scan_synth(12345, 0, 1, n, 8, oracle.synth_codes(24680, 0, nq, 8), k, n_procs=4)
+    kth1 = int((want[:, k - 1] >> np.uint64(32)).max())
+    misses = int(((want2[:, k - 1] >> np.uint64(32)) > kth1).sum())
     for g in range(G):
-        outs, n_x = ret[g]
+        outs, n_x, spec = ret[g]
         assert n_x >= 3                                  # bootstrap + one per step + the result rows
         np.testing.assert_array_equal(outs[0], want)
         np.testing.assert_array_equal(outs[1], want)
         np.testing.assert_array_equal(outs[2], want_r1)
+        assert spec == (kth1, misses), (spec, kth1, misses)      # the same guess and the same misses on both ranks
+        np.testing.assert_array_equal(outs[3], want2)

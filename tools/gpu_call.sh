@@ -1,4 +1,4 @@
 #!/bin/bash
 # scratch: the command list of the current gpurun call
 mkdir -p gpurun_out
-timeout 200 python bench.py --steps 10 --warmup 3 > gpurun_out/r02d_bench_final.json 2> gpurun_out/r02d_bench_final.err; echo rc=$?; tail -n 1 gpurun_out/r02d_bench_final.err | cut -c1-200; cut -c1-200 gpurun_out/r02d_bench_final.json
+timeout 70 python -m pytest tests/test_gpu_sharded.py -x -q -k "peer_windows" > gpurun_out/r02d_pytest3.log 2>&1; echo rc=$?; tail -n 6 gpurun_out/r02d_pytest3.log | cut -c1-300
